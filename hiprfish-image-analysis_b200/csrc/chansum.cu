@@ -1,0 +1,302 @@
+// K1: channel-sum prologue.  S[p] = sum_c cube[p, c]  (+ global max of S).
+//
+// Replaces np.sum(image_channel, axis=2) / np.max, syn/..._measurement.py:105-106.
+// HBM-bound: 4*C bytes read per pixel, 4 (or 8) written.  The (npix, C) cube is a flat
+// stream; pixel rows are 4*C = 380 bytes (C = 95), so no tensor map with a channel-sized box is
+// legal (inner box bytes must be a multiple of 16).  Instead a persistent CTA per SM runs a
+// ring of 1-D bulk async copies (cp.async.bulk -> UBLKCP, the TMA engine) of whole pixel
+// chunks (128 px * 380 B = 48,640 B, a multiple of 16) into shared memory, completion signalled
+// through mbarriers.  Consumer threads then sum one pixel each straight out of shared
+// memory: thread t reads words t*C + c, and with C odd the 32 lanes of a warp hit 32 distinct
+// banks.  Sums are accumulated in float64 (four independent chains) so the float32 result is
+// the correctly rounded sum; the stencil that follows amplifies any error by S/range.
+#include "hipr_common.cuh"
+
+namespace hipr {
+
+constexpr int CS_GROUP_THREADS = 128;  // one consumer thread per pixel of a chunk
+constexpr int CS_GROUPS = 2;           // consumer groups; chunk `it` goes to group it % 2
+constexpr int CS_THREADS = CS_GROUPS * CS_GROUP_THREADS + 32;  // + one producer warp
+constexpr int CS_MAX_STAGES = 8;
+constexpr int CS_SMEM_BUDGET = 227 * 1024 - 1024;
+
+template <typename OutT>
+__global__ void __launch_bounds__(CS_THREADS, 1)
+chansum_bulk_kernel(const float *__restrict__ cube, int64_t nchunks, int C, int cpx, int stages,
+                    OutT *__restrict__ out, unsigned long long *__restrict__ maxkey) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const uint32_t stage_bytes = (uint32_t)cpx * (uint32_t)C * 4u;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);
+    uint64_t *empty = full + CS_MAX_STAGES;
+    float *ring = reinterpret_cast<float *>(smem_raw + 128);
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    if (tid == 0) {
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], CS_GROUP_THREADS / 32);
+        }
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    if (warp == CS_GROUPS * (CS_GROUP_THREADS / 32)) {
+        // ---- producer: one elected lane keeps `stages` bulk copies in flight
+        if ((tid & 31) == 0) {
+            const uint64_t pol = policy_evict_first();
+            int s = 0;
+            uint32_t round = 0;
+            for (int64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+                if (round > 0) mbar_wait(&empty[s], (round - 1) & 1);
+                mbar_expect_tx(&full[s], stage_bytes);
+                bulk_g2s(reinterpret_cast<unsigned char *>(ring) + (size_t)s * stage_bytes,
+                         cube + chunk * (int64_t)cpx * C, stage_bytes, &full[s], pol);
+                if (++s == stages) { s = 0; ++round; }
+            }
+        }
+        return;
+    }
+
+    // ---- consumers
+    const int g = warp / (CS_GROUP_THREADS / 32);
+    const int t = tid - g * CS_GROUP_THREADS;
+    double vmax = -__longlong_as_double(0x7ff0000000000000ll);  // -inf
+    double vmin = __longlong_as_double(0x7ff0000000000000ll);
+    int64_t it = 0;
+    for (int64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x, ++it) {
+        if ((int)(it % CS_GROUPS) != g) continue;
+        const int s = (int)(it % stages);
+        const uint32_t parity = (uint32_t)((it / stages) & 1);
+        mbar_wait(&full[s], parity);
+        if (t < cpx) {
+            const float *px = ring + (size_t)s * (stage_bytes >> 2) + (size_t)t * C;
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            int c = 0;
+#pragma unroll 4
+            for (; c + 3 < C; c += 4) {
+                a0 += (double)px[c];
+                a1 += (double)px[c + 1];
+                a2 += (double)px[c + 2];
+                a3 += (double)px[c + 3];
+            }
+            for (; c < C; ++c) a0 += (double)px[c];
+            const double sum = (a0 + a1) + (a2 + a3);
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(&empty[s]);
+            out[chunk * cpx + t] = (OutT)sum;
+            vmax = fmax(vmax, (double)(OutT)sum);
+            vmin = fmin(vmin, (double)(OutT)sum);
+        } else {
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(&empty[s]);
+        }
+    }
+    if (maxkey != nullptr) {
+        vmax = warp_max(vmax);
+        vmin = -warp_max(-vmin);
+        if ((tid & 31) == 0) {
+            atomicMax(maxkey, (unsigned long long)key_of_double(vmax));
+            atomicMin(maxkey + 1, (unsigned long long)key_of_double(vmin));
+        }
+    }
+}
+
+// Generic path (tails, unaligned bases, flat-field divide): one warp per pixel, lanes stride
+// the channels (coalesced 128-byte requests), float64 butterfly reduction.
+template <typename OutT>
+__global__ void __launch_bounds__(256)
+chansum_warp_kernel(const float *__restrict__ cube, const float *__restrict__ calib, int64_t p0,
+                    int64_t p1, int C, OutT *__restrict__ out,
+                    unsigned long long *__restrict__ maxkey) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    double vmax = -__longlong_as_double(0x7ff0000000000000ll);
+    double vmin = __longlong_as_double(0x7ff0000000000000ll);
+    for (int64_t p = p0 + warp0; p < p1; p += nwarps) {
+        const float *px = cube + p * C;
+        double a = 0.0;
+        if (calib == nullptr) {
+            for (int c = lane; c < C; c += 32) a += (double)ldg_stream(px + c);
+        } else {
+            const float *cl = calib + p * C;
+            // float64 quotient of the float32 inputs, as numpy computes image/calibration
+            for (int c = lane; c < C; c += 32) a += (double)ldg_stream(px + c) / (double)ldg_stream(cl + c);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0) {
+            out[p] = (OutT)a;
+            vmax = fmax(vmax, (double)(OutT)a);
+            vmin = fmin(vmin, (double)(OutT)a);
+        }
+    }
+    if (maxkey != nullptr) {
+        vmax = warp_max(vmax);
+        vmin = -warp_max(-vmin);
+        if (lane == 0) {
+            atomicMax(maxkey, (unsigned long long)key_of_double(vmax));
+            atomicMin(maxkey + 1, (unsigned long long)key_of_double(vmin));
+        }
+    }
+}
+
+template <typename T>
+__global__ void normalize_kernel(T *__restrict__ s, int64_t n, const unsigned long long *__restrict__ maxkey) {
+    const T m = (T)double_of_key(*maxkey);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x)
+        s[i] = s[i] / m;
+}
+
+__global__ void normalize_cast_kernel(const double *__restrict__ s, int64_t n,
+                                      const unsigned long long *__restrict__ maxkey, float *__restrict__ out) {
+    const double m = maxkey ? double_of_key(*maxkey) : 1.0;   // NULL: plain float64 -> float32 cast
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = (float)(s[i] / m);
+}
+
+// global min / max of an image as order-preserving keys (for the fixed-point stencil)
+template <typename T>
+__global__ void __launch_bounds__(256)
+image_range_kernel(const T *__restrict__ a, int64_t n, unsigned long long *__restrict__ range) {
+    double vmax = -__longlong_as_double(0x7ff0000000000000ll);
+    double vmin = __longlong_as_double(0x7ff0000000000000ll);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const double v = (double)a[i];
+        vmax = fmax(vmax, v);
+        vmin = fmin(vmin, v);
+    }
+    vmax = warp_max(vmax);
+    vmin = -warp_max(-vmin);
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(range, (unsigned long long)key_of_double(vmax));
+        atomicMin(range + 1, (unsigned long long)key_of_double(vmin));
+    }
+}
+
+__global__ void maxkey_decode_kernel(const unsigned long long *__restrict__ k, double *__restrict__ out) {
+    *out = double_of_key(*k);
+}
+
+template <typename OutT>
+static int chansum_launch(const float *cube, const float *calib, int64_t npix, int C, OutT *out,
+                          unsigned long long *maxkey, cudaStream_t st) {
+    int64_t done = 0;
+    const bool aligned = (((uintptr_t)cube) & 15u) == 0;
+    if (calib == nullptr && aligned) {
+        int cpx = 0;
+        for (int cand = 128; cand >= 32; cand -= 32) {
+            if ((int64_t)cand * C * 4 * 4 <= CS_SMEM_BUDGET - 128) { cpx = cand; break; }
+        }
+        if (cpx > 0 && npix >= cpx) {
+            const int64_t stage_bytes = (int64_t)cpx * C * 4;
+            int stages = (int)((CS_SMEM_BUDGET - 128) / stage_bytes);
+            if (stages > CS_MAX_STAGES) stages = CS_MAX_STAGES;
+            const int64_t nchunks = npix / cpx;
+            const size_t smem = 128 + (size_t)stages * stage_bytes;
+            static bool attr_done[2] = {false, false};
+            auto kern = chansum_bulk_kernel<OutT>;
+            if (!attr_done[sizeof(OutT) == 8]) {
+                HIPR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               CS_SMEM_BUDGET));
+                attr_done[sizeof(OutT) == 8] = true;
+            }
+            int64_t grid = sm_count();
+            if (grid > nchunks) grid = nchunks;
+            kern<<<(unsigned)grid, CS_THREADS, smem, st>>>(cube, nchunks, C, cpx, stages, out, maxkey);
+            int e = after_launch();
+            if (e) return e;
+            done = nchunks * cpx;
+        }
+    }
+    if (done < npix) {
+        const int64_t rest = npix - done;
+        int64_t blocks = (rest + 7) / 8;  // 8 warps per block, one pixel per warp per trip
+        const int64_t cap = (int64_t)sm_count() * 8;
+        if (blocks > cap) blocks = cap;
+        chansum_warp_kernel<OutT><<<(unsigned)blocks, 256, 0, st>>>(cube, calib, done, npix, C, out, maxkey);
+        int e = after_launch();
+        if (e) return e;
+    }
+    return HIPR_OK;
+}
+
+// used by the host-buffer pipeline: one band of rows, max key accumulated (not reset)
+int chansum_band(const float *cube, int64_t npix, int C, double *out, unsigned long long *maxkey, cudaStream_t st) {
+    return chansum_launch<double>(cube, nullptr, npix, C, out, maxkey, st);
+}
+
+}  // namespace hipr
+
+using namespace hipr;
+
+extern "C" int hipr_chansum(const float *cube_dev, const float *calib_dev, int64_t npix, int C,
+                            void *sum_dev, int sum_dtype, uint64_t *maxkey_dev /* [2]: max, min */, void *stream) {
+    if (!cube_dev || !sum_dev || npix <= 0 || C <= 0) return HIPR_E_ARG;
+    if (sum_dtype != HIPR_F32 && sum_dtype != HIPR_F64) return HIPR_E_DTYPE;
+    if ((((uintptr_t)cube_dev) & 3u) || (calib_dev && (((uintptr_t)calib_dev) & 3u))) return HIPR_E_ALIGN;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (maxkey_dev) {
+        HIPR_CUDA(cudaMemsetAsync(maxkey_dev, 0x00, sizeof(uint64_t), st));      // max key: below all
+        HIPR_CUDA(cudaMemsetAsync(maxkey_dev + 1, 0xff, sizeof(uint64_t), st));  // min key: above all
+    }
+    unsigned long long *mk = reinterpret_cast<unsigned long long *>(maxkey_dev);
+    if (sum_dtype == HIPR_F32)
+        return chansum_launch<float>(cube_dev, calib_dev, npix, C, (float *)sum_dev, mk, st);
+    return chansum_launch<double>(cube_dev, calib_dev, npix, C, (double *)sum_dev, mk, st);
+}
+
+extern "C" int hipr_normalize(void *sum_dev, int sum_dtype, int64_t npix, const uint64_t *maxkey_dev,
+                              void *stream) {
+    if (!sum_dev || !maxkey_dev || npix <= 0) return HIPR_E_ARG;
+    if (sum_dtype != HIPR_F32 && sum_dtype != HIPR_F64) return HIPR_E_DTYPE;
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t blocks = (npix + 1023) / 1024;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    const unsigned long long *mk = reinterpret_cast<const unsigned long long *>(maxkey_dev);
+    if (sum_dtype == HIPR_F32)
+        normalize_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((float *)sum_dev, npix, mk);
+    else
+        normalize_kernel<double><<<(unsigned)blocks, 256, 0, st>>>((double *)sum_dev, npix, mk);
+    return after_launch();
+}
+
+extern "C" int hipr_maxkey_decode(const uint64_t *maxkey_dev, double *max_dev, void *stream) {
+    if (!maxkey_dev || !max_dev) return HIPR_E_ARG;
+    maxkey_decode_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const unsigned long long *>(maxkey_dev), max_dev);
+    return after_launch();
+}
+
+extern "C" int hipr_normalize_cast(const double *sum_dev, int64_t npix, const uint64_t *maxkey_dev, float *out_dev,
+                                   void *stream) {
+    if (!sum_dev || !out_dev || npix <= 0) return HIPR_E_ARG;
+    int64_t blocks = (npix + 1023) / 1024;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    normalize_cast_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        sum_dev, npix, reinterpret_cast<const unsigned long long *>(maxkey_dev), out_dev);
+    return after_launch();
+}
+
+extern "C" int hipr_image_range(const void *image_dev, int dtype, int64_t n, uint64_t *range_dev, void *stream) {
+    if (!image_dev || !range_dev || n <= 0) return HIPR_E_ARG;
+    if (dtype != HIPR_F32 && dtype != HIPR_F64) return HIPR_E_DTYPE;
+    cudaStream_t st = (cudaStream_t)stream;
+    HIPR_CUDA(cudaMemsetAsync(range_dev, 0x00, sizeof(uint64_t), st));
+    HIPR_CUDA(cudaMemsetAsync(range_dev + 1, 0xff, sizeof(uint64_t), st));
+    int64_t blocks = (n + 2047) / 2048;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    unsigned long long *rg = reinterpret_cast<unsigned long long *>(range_dev);
+    if (dtype == HIPR_F32)
+        image_range_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((const float *)image_dev, n, rg);
+    else
+        image_range_kernel<double><<<(unsigned)blocks, 256, 0, st>>>((const double *)image_dev, n, rg);
+    return after_launch();
+}

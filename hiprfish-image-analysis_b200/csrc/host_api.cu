@@ -1,0 +1,254 @@
+// ABI housekeeping and the host-buffer entry points: what a numpy caller binds.  The cube is
+// streamed host -> device in row bands on a copy stream while the channel sum (or the per-cell
+// accumulation) of the previous band runs on a compute stream, so the end-to-end time is the
+// PCIe time of the cube plus a short tail.
+#include <mutex>
+#include <string.h>
+#include "hipr_common.cuh"
+
+namespace hipr {
+
+std::atomic<int64_t> g_launches{0};
+
+int chansum_band(const float *cube, int64_t npix, int C, double *out, unsigned long long *maxkey, cudaStream_t st);
+
+constexpr int NBUF = 3;
+struct Workspace {
+    std::mutex mu;
+    cudaStream_t copy = nullptr, comp = nullptr;
+    cudaEvent_t copied[NBUF] = {}, freed[NBUF] = {}, done = nullptr;
+    void *band[NBUF] = {};
+    size_t band_bytes = 0;
+    void *aux[6] = {};
+    size_t aux_bytes[6] = {};
+    bool ready = false;
+};
+static Workspace g_ws;
+
+static int ws_init(Workspace &w) {
+    if (w.ready) return HIPR_OK;
+    HIPR_CUDA(cudaStreamCreateWithFlags(&w.copy, cudaStreamNonBlocking));
+    HIPR_CUDA(cudaStreamCreateWithFlags(&w.comp, cudaStreamNonBlocking));
+    for (int i = 0; i < NBUF; ++i) {
+        HIPR_CUDA(cudaEventCreateWithFlags(&w.copied[i], cudaEventDisableTiming));
+        HIPR_CUDA(cudaEventCreateWithFlags(&w.freed[i], cudaEventDisableTiming));
+    }
+    HIPR_CUDA(cudaEventCreateWithFlags(&w.done, cudaEventDisableTiming));
+    w.ready = true;
+    return HIPR_OK;
+}
+static int ws_bands(Workspace &w, size_t bytes) {
+    if (bytes <= w.band_bytes) return HIPR_OK;
+    for (int i = 0; i < NBUF; ++i) {
+        if (w.band[i]) cudaFree(w.band[i]);
+        w.band[i] = nullptr;
+    }
+    w.band_bytes = 0;
+    for (int i = 0; i < NBUF; ++i) HIPR_CUDA(cudaMalloc(&w.band[i], bytes));
+    w.band_bytes = bytes;
+    return HIPR_OK;
+}
+static int ws_aux(Workspace &w, int slot, size_t bytes) {
+    if (bytes <= w.aux_bytes[slot]) return HIPR_OK;
+    if (w.aux[slot]) cudaFree(w.aux[slot]);
+    w.aux[slot] = nullptr;
+    w.aux_bytes[slot] = 0;
+    HIPR_CUDA(cudaMalloc(&w.aux[slot], bytes));
+    w.aux_bytes[slot] = bytes;
+    return HIPR_OK;
+}
+
+// rows per band so that a band is ~32 MiB and a whole number of rows
+static int band_rows(int64_t row_bytes, int64_t nrows) {
+    int64_t r = (32ll << 20) / (row_bytes > 0 ? row_bytes : 1);
+    if (r < 1) r = 1;
+    if (r > nrows) r = nrows;
+    return (int)r;
+}
+
+}  // namespace hipr
+
+using namespace hipr;
+
+extern "C" int hipr_abi_version(void) { return HIPR_ABI_VERSION; }
+
+extern "C" int64_t hipr_launch_count(void) { return g_launches.load(); }
+
+extern "C" int hipr_sm_count(void) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return HIPR_E_NODEVICE;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return HIPR_E_NODEVICE;
+    return n;
+}
+
+extern "C" const char *hipr_error_string(int code) {
+    switch (code) {
+        case HIPR_OK: return "ok";
+        case HIPR_E_ARG: return "invalid argument (null pointer or non-positive size)";
+        case HIPR_E_DTYPE: return "unsupported dtype code";
+        case HIPR_E_PATCH: return "patch_size must be odd, 3..31, and no larger than the image";
+        case HIPR_E_TABLE: return "line table entry outside the patch, or table too large";
+        case HIPR_E_FLAVOUR: return "unknown epilogue flavour for this entry point";
+        case HIPR_E_ALIGN: return "pointer not aligned to its element type";
+        case HIPR_E_RANGE: return "size exceeds the index range or the caller's capacity";
+        case HIPR_E_NODEVICE: return "no CUDA device";
+        default: break;
+    }
+    if (code > 0) return cudaGetErrorString((cudaError_t)code);
+    return "unknown error";
+}
+
+extern "C" int hipr_host_alloc(void **ptr, int64_t bytes) {
+    if (!ptr || bytes <= 0) return HIPR_E_ARG;
+    HIPR_CUDA(cudaHostAlloc(ptr, (size_t)bytes, cudaHostAllocDefault));
+    return HIPR_OK;
+}
+extern "C" int hipr_host_free(void *ptr) {
+    if (!ptr) return HIPR_OK;
+    HIPR_CUDA(cudaFreeHost(ptr));
+    return HIPR_OK;
+}
+extern "C" int hipr_host_release_workspace(void) {
+    Workspace &w = g_ws;
+    std::lock_guard<std::mutex> lock(w.mu);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < NBUF; ++i) {
+        if (w.band[i]) cudaFree(w.band[i]);
+        w.band[i] = nullptr;
+    }
+    w.band_bytes = 0;
+    for (int i = 0; i < 6; ++i) {
+        if (w.aux[i]) cudaFree(w.aux[i]);
+        w.aux[i] = nullptr;
+        w.aux_bytes[i] = 0;
+    }
+    return HIPR_OK;
+}
+
+extern "C" int hipr_neighbor2d_host(const float *cube_host, int H, int W, int C, int patch_size, int n_dirs,
+                                    const int32_t *table_host, int flavour, float *score_host, float *sum_host) {
+    if (!cube_host || !score_host || H < 1 || W < 1 || C < 1) return HIPR_E_ARG;
+    Workspace &w = g_ws;
+    std::lock_guard<std::mutex> lock(w.mu);
+    int e = ws_init(w);
+    if (e) return e;
+    const int64_t row_bytes = (int64_t)W * C * 4;
+    const int rows = band_rows(row_bytes, H);
+    if ((e = ws_bands(w, (size_t)rows * row_bytes))) return e;
+    const size_t img_bytes = (size_t)H * W * 4;
+    if ((e = ws_aux(w, 0, 4 * img_bytes))) return e;  // float64 sum image (+ float64 score, general parameters)
+    if ((e = ws_aux(w, 1, img_bytes))) return e;      // score, then the float32 normalised sum
+    if ((e = ws_aux(w, 2, 64))) return e;             // max / min keys
+    double *sum_dev = (double *)w.aux[0];
+    float *score_dev = (float *)w.aux[1];
+    unsigned long long *key = (unsigned long long *)w.aux[2];
+    HIPR_CUDA(cudaMemsetAsync(key, 0x00, 8, w.comp));
+    HIPR_CUDA(cudaMemsetAsync(key + 1, 0xff, 8, w.comp));
+    int b = 0;
+    for (int r0 = 0; r0 < H; r0 += rows, ++b) {
+        const int nr = (H - r0 < rows) ? H - r0 : rows;
+        const int slot = b % NBUF;
+        if (b >= NBUF) HIPR_CUDA(cudaStreamWaitEvent(w.copy, w.freed[slot], 0));
+        HIPR_CUDA(cudaMemcpyAsync(w.band[slot], cube_host + (int64_t)r0 * W * C, (size_t)nr * row_bytes,
+                                  cudaMemcpyHostToDevice, w.copy));
+        HIPR_CUDA(cudaEventRecord(w.copied[slot], w.copy));
+        HIPR_CUDA(cudaStreamWaitEvent(w.comp, w.copied[slot], 0));
+        if ((e = chansum_band((const float *)w.band[slot], (int64_t)nr * W, C, sum_dev + (int64_t)r0 * W, key, w.comp)))
+            return e;
+        HIPR_CUDA(cudaEventRecord(w.freed[slot], w.comp));
+    }
+    // fixed-point stencil for the (11, 9) table every pipeline uses; float64 kernel otherwise
+    e = hipr_lne2d_q(sum_dev, H, W, W, 0, HIPR_F64, patch_size, n_dirs, table_host, flavour, (const uint64_t *)key,
+                     score_dev, w.comp);
+    if (e == HIPR_E_TABLE && !(patch_size == 11 && n_dirs == 9)) {
+        // general parameters: float64 stencil into the upper half of aux[0], then cast
+        double *score64 = sum_dev + (size_t)H * W;
+        if ((e = hipr_lne2d(sum_dev, H, W, W, 0, HIPR_F64, patch_size, n_dirs, table_host, flavour,
+                            (const uint64_t *)key, score64, w.comp)))
+            return e;
+        e = hipr_normalize_cast(score64, (int64_t)H * W, nullptr, score_dev, w.comp);
+    }
+    if (e) return e;
+    HIPR_CUDA(cudaMemcpyAsync(score_host, score_dev, img_bytes, cudaMemcpyDeviceToHost, w.comp));
+    if (sum_host) {
+        if ((e = hipr_normalize_cast(sum_dev, (int64_t)H * W, (const uint64_t *)key, score_dev, w.comp))) return e;
+        HIPR_CUDA(cudaMemcpyAsync(sum_host, score_dev, img_bytes, cudaMemcpyDeviceToHost, w.comp));
+    }
+    HIPR_CUDA(cudaStreamSynchronize(w.comp));
+    return HIPR_OK;
+}
+
+extern "C" int hipr_cell_spectra_host(const float *cube_host, const void *labels_host, int label_bytes, int64_t npix,
+                                      int C, int64_t capacity, int64_t *n_cells, int64_t *labels_out,
+                                      int64_t *area_out, double *avgint_out, double *avgint_norm_out) {
+    if (!cube_host || !labels_host || !n_cells || !labels_out || !area_out || !avgint_out || !avgint_norm_out ||
+        npix < 1 || C < 1 || capacity < 0)
+        return HIPR_E_ARG;
+    if (label_bytes != 4 && label_bytes != 8) return HIPR_E_DTYPE;
+    Workspace &w = g_ws;
+    std::lock_guard<std::mutex> lock(w.mu);
+    int e = ws_init(w);
+    if (e) return e;
+    // labels first (small), max label back to the host to size the accumulators
+    if ((e = ws_aux(w, 3, (size_t)npix * label_bytes))) return e;
+    if ((e = ws_aux(w, 2, 64))) return e;
+    void *labels_dev = w.aux[3];
+    int64_t *scalar_dev = (int64_t *)w.aux[2];
+    HIPR_CUDA(cudaMemcpyAsync(labels_dev, labels_host, (size_t)npix * label_bytes, cudaMemcpyHostToDevice, w.comp));
+    if ((e = hipr_label_max(labels_dev, label_bytes, npix, scalar_dev, w.comp))) return e;
+    int64_t max_label = 0;
+    HIPR_CUDA(cudaMemcpyAsync(&max_label, scalar_dev, 8, cudaMemcpyDeviceToHost, w.comp));
+    HIPR_CUDA(cudaStreamSynchronize(w.comp));
+    *n_cells = 0;
+    if (max_label <= 0) return HIPR_OK;
+    const size_t sums_bytes = (size_t)(max_label + 1) * C * 8;
+    const size_t cnt_bytes = (size_t)(max_label + 1) * 4;
+    if ((e = ws_aux(w, 4, sums_bytes + cnt_bytes + 16))) return e;
+    double *sums = (double *)w.aux[4];
+    int32_t *counts = (int32_t *)((char *)w.aux[4] + sums_bytes);
+    HIPR_CUDA(cudaMemsetAsync(w.aux[4], 0, sums_bytes + cnt_bytes + 16, w.comp));
+    const int64_t px_bytes = (int64_t)C * 4;
+    int64_t band_px = (32ll << 20) / px_bytes;
+    band_px &= ~31ll;  // whole warps' worth of pixels per band
+    if (band_px < 32) band_px = 32;
+    if ((e = ws_bands(w, (size_t)band_px * px_bytes))) return e;
+    int b = 0;
+    for (int64_t p0 = 0; p0 < npix; p0 += band_px, ++b) {
+        const int64_t np = (npix - p0 < band_px) ? npix - p0 : band_px;
+        const int slot = b % NBUF;
+        if (b >= NBUF) HIPR_CUDA(cudaStreamWaitEvent(w.copy, w.freed[slot], 0));
+        HIPR_CUDA(cudaMemcpyAsync(w.band[slot], cube_host + p0 * C, (size_t)np * px_bytes, cudaMemcpyHostToDevice,
+                                  w.copy));
+        HIPR_CUDA(cudaEventRecord(w.copied[slot], w.copy));
+        HIPR_CUDA(cudaStreamWaitEvent(w.comp, w.copied[slot], 0));
+        if ((e = hipr_cell_spectra_accumulate((const float *)w.band[slot], (const char *)labels_dev + p0 * label_bytes,
+                                              label_bytes, np, C, max_label, sums, counts, nullptr, w.comp)))
+            return e;
+        HIPR_CUDA(cudaEventRecord(w.freed[slot], w.comp));
+    }
+    // finalize into device scratch sized by max_label, then copy the valid rows back
+    const size_t row_bytes = (size_t)C * 8;
+    const size_t fin_bytes = 16 + (size_t)max_label * (16 + 2 * row_bytes);
+    if ((e = ws_aux(w, 5, fin_bytes))) return e;
+    char *fin = (char *)w.aux[5];
+    int32_t *n_dev = (int32_t *)fin;
+    int64_t *lab_dev = (int64_t *)(fin + 16);
+    int64_t *area_dev = lab_dev + max_label;
+    double *avg_dev = (double *)(area_dev + max_label);
+    double *norm_dev = avg_dev + (size_t)max_label * C;
+    if ((e = hipr_cell_spectra_finalize(sums, counts, max_label, C, n_dev, lab_dev, area_dev, avg_dev, norm_dev,
+                                        w.comp)))
+        return e;
+    int32_t n = 0;
+    HIPR_CUDA(cudaMemcpyAsync(&n, n_dev, 4, cudaMemcpyDeviceToHost, w.comp));
+    HIPR_CUDA(cudaStreamSynchronize(w.comp));
+    *n_cells = n;
+    if (n > capacity) return HIPR_E_RANGE;
+    if (n == 0) return HIPR_OK;
+    HIPR_CUDA(cudaMemcpyAsync(labels_out, lab_dev, (size_t)n * 8, cudaMemcpyDeviceToHost, w.comp));
+    HIPR_CUDA(cudaMemcpyAsync(area_out, area_dev, (size_t)n * 8, cudaMemcpyDeviceToHost, w.comp));
+    HIPR_CUDA(cudaMemcpyAsync(avgint_out, avg_dev, (size_t)n * row_bytes, cudaMemcpyDeviceToHost, w.comp));
+    HIPR_CUDA(cudaMemcpyAsync(avgint_norm_out, norm_dev, (size_t)n * row_bytes, cudaMemcpyDeviceToHost, w.comp));
+    HIPR_CUDA(cudaStreamSynchronize(w.comp));
+    return HIPR_OK;
+}

@@ -1,0 +1,274 @@
+// 3-D stencils (biofilm z-stacks), bio/neighbor.pyx.
+//   line_profile_3d : literal 5-D gather, bio/neighbor.pyx:171-180 (shares K2's gather kernel)
+//   lne3d_dirs      : line_profile_memory_efficient_v2, bio/neighbor.pyx:246-262
+//   lne3d           : stencil + epilogue (F2 / F3 / ME2 / V3)
+// Fast path: P = 11, 72 directions; a (TX+10) x (8+10) x (32+10) brick of the volume sits in
+// shared memory (z fastest, lanes along z: conflict-free), each thread walks TX voxels.  The
+// 792-entry offset table rides in the kernel parameter bank.  This kernel is shared-memory /
+// min-max-ALU bound (792 samples + a 72-value rank selection per voxel), not HBM bound.
+#include "hipr_common.cuh"
+#include "lne_math.cuh"
+
+namespace hipr {
+
+template <typename T>
+int gather_launch(const T *src, int64_t stride_a, int64_t stride_b, int inner, int64_t nrows, int rowlen,
+                  int K, const int *lin, T *out, cudaStream_t st);
+int check_table(const int32_t *table, int n_dirs, int P, int ndim);
+
+struct Table3D {
+    int off[HIPR_MAX_TABLE];
+};
+
+constexpr int L3_P = 11, L3_T = 72, L3_HALF = 5;
+constexpr int L3_TY = 8, L3_TZ = 32;
+constexpr int L3_SY = L3_TY + L3_P - 1;  // 18
+constexpr int L3_SZ = L3_TZ + L3_P - 1;  // 42
+
+// MODE 0: write the 72 per-direction values (me_v2); MODE 1: write the fused score.
+template <typename T, int FLAVOUR, int MODE, int TX>
+__global__ void __launch_bounds__(256)
+lne3d_p11t72_kernel(const T *__restrict__ vol, int Xs, int Ys, int Zs, int src_off, int X, int Y, int Z,
+                    const __grid_constant__ Table3D tab,  // (dx * SY + dy) * SZ + dz, patch coords
+                    const unsigned long long *__restrict__ maxkey, T *__restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw3[];
+    T *tile = reinterpret_cast<T *>(smem_raw3);
+    constexpr int SX = TX + L3_P - 1;
+    const int nzb = (Z + L3_TZ - 1) / L3_TZ;
+    const int z0 = (blockIdx.x % nzb) * L3_TZ;
+    const int y0 = (blockIdx.x / nzb) * L3_TY;
+    const int x0 = blockIdx.y * TX;
+    const bool scale = (maxkey != nullptr);
+    const T vmax = scale ? (T)double_of_key(*maxkey) : (T)1;
+    for (int i = threadIdx.x; i < SX * L3_SY * L3_SZ; i += 256) {
+        const int lz = i % L3_SZ, rest = i / L3_SZ;
+        const int ly = rest % L3_SY, lx = rest / L3_SY;
+        int sx = x0 + lx - L3_HALF + src_off, sy = y0 + ly - L3_HALF + src_off, sz = z0 + lz - L3_HALF + src_off;
+        sx = min(max(sx, 0), Xs - 1);
+        sy = min(max(sy, 0), Ys - 1);
+        sz = min(max(sz, 0), Zs - 1);
+        T v = vol[((int64_t)sx * Ys + sy) * Zs + sz];
+        if (scale) v = Num<T>::div(v, vmax);
+        if (FLAVOUR == HIPR_FLAVOUR_F2) v = nan_to_num<T>(v);
+        tile[i] = v;
+    }
+    __syncthreads();
+    const int tz = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int z = z0 + tz, y = y0 + ty;
+    if (z >= Z || y >= Y) return;
+#pragma unroll 1
+    for (int lx = 0; lx < TX; ++lx) {
+        const int x = x0 + lx;
+        if (x >= X) break;
+        const T *base = tile + (lx * L3_SY + ty) * L3_SZ + tz;
+        T r[L3_T];
+#pragma unroll
+        for (int t = 0; t < L3_T; ++t) {
+            T mn = base[tab.off[t * L3_P]], mx = mn, centre = mn;
+            bool bad = (mn != mn);
+#pragma unroll
+            for (int li = 1; li < L3_P; ++li) {
+                const T s = base[tab.off[t * L3_P + li]];
+                mn = Num<T>::mn(mn, s);
+                mx = Num<T>::mx(mx, s);
+                if (li == L3_HALF) centre = s;
+                if (FLAVOUR != HIPR_FLAVOUR_F2) bad |= (s != s);
+            }
+            r[t] = line_rel<T, FLAVOUR>(centre, mn, mx, bad);
+        }
+        const int64_t v = ((int64_t)x * Y + y) * Z + z;
+        if (MODE == 0) {
+            T *o = out + v * L3_T;
+#pragma unroll
+            for (int t = 0; t < L3_T; ++t) o[t] = r[t];
+        } else {
+            out[v] = reduce_dirs<T, L3_T, FLAVOUR>(r);
+        }
+    }
+}
+
+// Generic path: any table; thread per voxel from global memory.  `flat` != 0 reproduces the
+// v3 function's flat addressing: table entries may leave the patch, the address is taken in
+// the padded buffer and a read past its end gives NaN (undefined behaviour in the reference).
+template <typename T>
+__global__ void __launch_bounds__(128)
+lne3d_generic_kernel(const T *__restrict__ vol, int Xs, int Ys, int Zs, int src_off, int X, int Y, int Z,
+                     int P, int Tn, const int *__restrict__ tab /* (t, li, 3) device */, int flavour, int mode,
+                     int flat, const unsigned long long *__restrict__ maxkey, T *__restrict__ out) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)X * Y * Z) return;
+    const int z = (int)(idx % Z);
+    const int64_t rest = idx / Z;
+    const int y = (int)(rest % Y), x = (int)(rest / Y);
+    const int half = (P - 1) / 2;
+    const bool scale = (maxkey != nullptr);
+    const T vmax = scale ? (T)double_of_key(*maxkey) : (T)1;
+    const bool n2n = (flavour == HIPR_FLAVOUR_F2);
+    const int64_t nvox = (int64_t)Xs * Ys * Zs;
+    T r[HIPR_MAX_DIRS];
+    for (int t = 0; t < Tn; ++t) {
+        T mn = (T)0, mx = (T)0, centre = (T)0;
+        bool bad = false;
+        for (int li = 0; li < P; ++li) {
+            const int *o = tab + (t * P + li) * 3;
+            T s;
+            if (flat) {
+                const int64_t a = ((int64_t)(x + o[0]) * Ys + (y + o[1])) * Zs + (z + o[2]);
+                s = (a >= 0 && a < nvox) ? vol[a] : Num<T>::nan();
+            } else {
+                int sx = x + o[0] - half + src_off, sy = y + o[1] - half + src_off, sz = z + o[2] - half + src_off;
+                sx = min(max(sx, 0), Xs - 1);
+                sy = min(max(sy, 0), Ys - 1);
+                sz = min(max(sz, 0), Zs - 1);
+                s = vol[((int64_t)sx * Ys + sy) * Zs + sz];
+            }
+            if (scale) s = Num<T>::div(s, vmax);
+            if (n2n) s = nan_to_num<T>(s);
+            bad |= (s != s);
+            if (li == 0) { mn = s; mx = s; }
+            else { mn = Num<T>::mn(mn, s); mx = Num<T>::mx(mx, s); }
+            if (li == half) centre = s;
+        }
+        switch (flavour) {
+            case HIPR_FLAVOUR_F2: r[t] = line_rel<T, HIPR_FLAVOUR_F2>(centre, mn, mx, bad); break;
+            case HIPR_FLAVOUR_F3: r[t] = line_rel<T, HIPR_FLAVOUR_F3>(centre, mn, mx, bad); break;
+            default: r[t] = line_rel<T, HIPR_FLAVOUR_ME2>(centre, mn, mx, bad); break;
+        }
+    }
+    if (mode == 0) {
+        for (int t = 0; t < Tn; ++t) out[idx * Tn + t] = r[t];
+    } else {
+        out[idx] = reduce_dirs_runtime<T>(r, Tn, flavour);
+    }
+}
+
+int upload_offsets(const int *lin, int n, cudaStream_t st, const int **dev_out);
+
+template <typename T, int FLAVOUR, int MODE>
+static int launch_fast3d(const T *vol, int Xs, int Ys, int Zs, int src_off, int X, int Y, int Z, const Table3D &tab,
+                         const unsigned long long *maxkey, T *out, cudaStream_t st) {
+    constexpr int TX = (sizeof(T) == 4) ? 8 : 4;
+    constexpr int SX = TX + L3_P - 1;
+    const size_t smem = (size_t)SX * L3_SY * L3_SZ * sizeof(T);
+    auto kern = lne3d_p11t72_kernel<T, FLAVOUR, MODE, TX>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        HIPR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    const int nzb = (Z + L3_TZ - 1) / L3_TZ, nyb = (Y + L3_TY - 1) / L3_TY, nxb = (X + TX - 1) / TX;
+    if ((int64_t)nzb * nyb > 0x7fffffffLL || nxb > 65535) return HIPR_E_RANGE;
+    dim3 grid((unsigned)(nzb * nyb), (unsigned)nxb);
+    kern<<<grid, 256, smem, st>>>(vol, Xs, Ys, Zs, src_off, X, Y, Z, tab, maxkey, out);
+    return after_launch();
+}
+
+template <typename T>
+static int lne3d_dispatch(const T *vol, int Xs, int Ys, int Zs, int padded, int P, int Tn, const int32_t *table,
+                          int flavour, int mode, const unsigned long long *maxkey, T *out, cudaStream_t st) {
+    const int X = padded ? Xs - (P - 1) : Xs, Y = padded ? Ys - (P - 1) : Ys, Z = padded ? Zs - (P - 1) : Zs;
+    const int src_off = padded ? (P - 1) / 2 : 0;
+    if (X < 1 || Y < 1 || Z < 1) return HIPR_E_PATCH;
+    const bool flat = (flavour == HIPR_FLAVOUR_V3);
+    if (flat && !padded) return HIPR_E_ARG;
+    bool in_patch = true;
+    for (int i = 0; i < Tn * P * 3; ++i)
+        if (table[i] < 0 || table[i] >= P) in_patch = false;
+    if (!in_patch && !flat) return HIPR_E_TABLE;
+    if (flat)
+        for (int i = 0; i < Tn * P * 3; ++i)
+            if (table[i] < -4 * P || table[i] > 4 * P) return HIPR_E_TABLE;
+    if (P == L3_P && Tn == L3_T && in_patch && !flat) {
+        Table3D tab;
+        for (int i = 0; i < Tn * P; ++i)
+            tab.off[i] = (table[3 * i] * L3_SY + table[3 * i + 1]) * L3_SZ + table[3 * i + 2];
+        if (mode == 0)
+            return launch_fast3d<T, HIPR_FLAVOUR_ME2, 0>(vol, Xs, Ys, Zs, src_off, X, Y, Z, tab, maxkey, out, st);
+        switch (flavour) {
+            case HIPR_FLAVOUR_F2: return launch_fast3d<T, HIPR_FLAVOUR_F2, 1>(vol, Xs, Ys, Zs, src_off, X, Y, Z, tab, maxkey, out, st);
+            case HIPR_FLAVOUR_F3: return launch_fast3d<T, HIPR_FLAVOUR_F3, 1>(vol, Xs, Ys, Zs, src_off, X, Y, Z, tab, maxkey, out, st);
+            case HIPR_FLAVOUR_ME2: return launch_fast3d<T, HIPR_FLAVOUR_ME2, 1>(vol, Xs, Ys, Zs, src_off, X, Y, Z, tab, maxkey, out, st);
+            default: return HIPR_E_FLAVOUR;
+        }
+    }
+    if (flavour != HIPR_FLAVOUR_F2 && flavour != HIPR_FLAVOUR_F3 && flavour != HIPR_FLAVOUR_ME2 && !flat)
+        return HIPR_E_FLAVOUR;
+    if (Tn * P * 3 > HIPR_MAX_TABLE * 3) return HIPR_E_TABLE;
+    // the generic kernel reads the (t, li, 3) table from global memory; cache it like K2's offsets
+    static int *tab_dev = nullptr;
+    static int tab_host[HIPR_MAX_TABLE * 3];
+    static int tab_n = 0;
+    const int n = Tn * P * 3;
+    if (!tab_dev) HIPR_CUDA(cudaMalloc(&tab_dev, sizeof(tab_host)));
+    if (tab_n != n || memcmp(tab_host, table, n * sizeof(int)) != 0) {
+        HIPR_CUDA(cudaDeviceSynchronize());  // a previous launch may still read the old table
+        HIPR_CUDA(cudaMemcpy(tab_dev, table, n * sizeof(int), cudaMemcpyHostToDevice));
+        memcpy(tab_host, table, n * sizeof(int));
+        tab_n = n;
+    }
+    const int64_t nv = (int64_t)X * Y * Z;
+    if ((nv + 127) / 128 > 0x7fffffffLL) return HIPR_E_RANGE;
+    lne3d_generic_kernel<T><<<(unsigned)((nv + 127) / 128), 128, 0, st>>>(vol, Xs, Ys, Zs, src_off, X, Y, Z, P, Tn,
+                                                                         tab_dev, flavour, mode, flat ? 1 : 0,
+                                                                         maxkey, out);
+    return after_launch();
+}
+
+}  // namespace hipr
+
+using namespace hipr;
+
+extern "C" int hipr_line_profile_3d(const void *volume_padded_dev, int Xp, int Yp, int Zp, int dtype, int patch_size,
+                                    int n_dirs, const int32_t *table_host, void *out_dev, void *stream) {
+    if (!volume_padded_dev || !out_dev) return HIPR_E_ARG;
+    if (dtype != HIPR_F32 && dtype != HIPR_F64) return HIPR_E_DTYPE;
+    int e = check_table(table_host, n_dirs, patch_size, 3);
+    if (e) return e;
+    const int P = patch_size, X = Xp - (P - 1), Y = Yp - (P - 1), Z = Zp - (P - 1);
+    if (X < 1 || Y < 1 || Z < 1) return HIPR_E_PATCH;
+    int lin[HIPR_MAX_TABLE];
+    for (int i = 0; i < n_dirs * P; ++i) {
+        const int a = table_host[3 * i], b = table_host[3 * i + 1], c = table_host[3 * i + 2];
+        if (a < 0 || a >= P || b < 0 || b >= P || c < 0 || c >= P) return HIPR_E_TABLE;
+        const int64_t l = ((int64_t)a * Yp + b) * Zp + c;
+        if (l > 0x7fffffffLL) return HIPR_E_RANGE;
+        lin[i] = (int)l;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t sa = (int64_t)Yp * Zp, sb = Zp;
+    if (dtype == HIPR_F32)
+        return gather_launch<float>((const float *)volume_padded_dev, sa, sb, Y, (int64_t)X * Y, Z, n_dirs * P, lin,
+                                    (float *)out_dev, st);
+    return gather_launch<double>((const double *)volume_padded_dev, sa, sb, Y, (int64_t)X * Y, Z, n_dirs * P, lin,
+                                 (double *)out_dev, st);
+}
+
+static int lne3d_entry(const void *volume_dev, int Xs, int Ys, int Zs, int padded, int dtype, int patch_size,
+                       int n_dirs, const int32_t *table_host, int flavour, int mode, const uint64_t *maxkey_dev,
+                       void *out_dev, void *stream) {
+    if (!volume_dev || !out_dev || Xs < 1 || Ys < 1 || Zs < 1) return HIPR_E_ARG;
+    if (dtype != HIPR_F32 && dtype != HIPR_F64) return HIPR_E_DTYPE;
+    int e = check_table(table_host, n_dirs, patch_size, 3);
+    if (e) return e;
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned long long *mk = reinterpret_cast<const unsigned long long *>(maxkey_dev);
+    if (dtype == HIPR_F32)
+        return lne3d_dispatch<float>((const float *)volume_dev, Xs, Ys, Zs, padded, patch_size, n_dirs, table_host,
+                                     flavour, mode, mk, (float *)out_dev, st);
+    return lne3d_dispatch<double>((const double *)volume_dev, Xs, Ys, Zs, padded, patch_size, n_dirs, table_host,
+                                  flavour, mode, mk, (double *)out_dev, st);
+}
+
+extern "C" int hipr_lne3d_dirs(const void *volume_dev, int Xs, int Ys, int Zs, int padded, int dtype, int patch_size,
+                               int n_dirs, const int32_t *table_host, const uint64_t *maxkey_dev, void *out_dev,
+                               void *stream) {
+    return lne3d_entry(volume_dev, Xs, Ys, Zs, padded, dtype, patch_size, n_dirs, table_host, HIPR_FLAVOUR_ME2, 0,
+                       maxkey_dev, out_dev, stream);
+}
+
+extern "C" int hipr_lne3d(const void *volume_dev, int Xs, int Ys, int Zs, int padded, int dtype, int patch_size,
+                          int n_dirs, const int32_t *table_host, int flavour, const uint64_t *maxkey_dev,
+                          void *out_dev, void *stream) {
+    return lne3d_entry(volume_dev, Xs, Ys, Zs, padded, dtype, patch_size, n_dirs, table_host, flavour, 1, maxkey_dev,
+                       out_dev, stream);
+}

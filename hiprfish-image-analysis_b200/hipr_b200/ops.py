@@ -1,0 +1,402 @@
+"""Device-resident operators: torch CUDA tensors in, torch CUDA tensors out, stream-ordered on
+torch's current stream.  torch is used for device memory and streams only; every kernel that
+runs here is one of libhipr_b200's.  No CPU fallback: CPU tensors are rejected.
+
+Reference blocks replaced (paths relative to the reference repository):
+  channel_sum       syn/hiprfish_imaging_multispecies_spectral_image_measurement.py:105-106
+  lne2d             eco/neighbor2d.pyx:56-63 + syn/...measurement.py:109-124 (F1), bio F2 / F3
+  neighbor2d_score  syn/...measurement.py:105-124 without the skimage denoise
+  line_profile_2d   eco/neighbor2d.pyx:8-64
+  line_profile_3d   bio/neighbor.pyx:115-181
+  lne3d_dirs        bio/neighbor.pyx:186-263
+  lne3d             bio/neighbor.pyx + bio/hiprfish_imaging_biofilm_analysis.py:812-817, 905-917, 1114-1125
+  cell_spectra      syn/...measurement.py:167-172
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import tables
+from ._lib import F32, F64, FLAVOURS, check, lib
+
+_DT = {torch.float32: F32, torch.float64: F64}
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _dev(t, name, dtypes=(torch.float32, torch.float64)):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a torch.Tensor on a CUDA device" % name)
+    if not t.is_cuda:
+        raise ValueError("%s must live on a CUDA device (there is no CPU path)" % name)
+    if t.dtype not in dtypes:
+        raise TypeError("%s: unsupported dtype %s" % (name, t.dtype))
+    return t.contiguous()
+
+
+def _tab_ptr(tab):
+    return tab.ctypes.data_as(C.c_void_p)
+
+
+def _flavour(f):
+    try:
+        return FLAVOURS[f]
+    except KeyError:
+        raise ValueError("unknown flavour %r (one of %s)" % (f, sorted(FLAVOURS)))
+
+
+class MaxKey:
+    """Two device scalars: max and min of an image as order-preserving keys (see hipr_b200.h)."""
+
+    def __init__(self, device):
+        self.key = torch.zeros(2, dtype=torch.int64, device=device)
+
+    def ptr(self):
+        return C.c_void_p(self.key.data_ptr())
+
+    def value(self):
+        out = torch.empty(1, dtype=torch.float64, device=self.key.device)
+        check(lib().hipr_maxkey_decode(self.ptr(), C.c_void_p(out.data_ptr()), _stream()), "maxkey_decode")
+        return out
+
+
+def channel_sum(cube, calibration=None, normalize=True, dtype=torch.float32, return_max=False):
+    """cube (..., C) float32 -> (...) sum over the last axis, divided by its global max when
+    `normalize` (image_registered_sum / np.max(...)).  Accumulation is float64."""
+    cube = _dev(cube, "cube", (torch.float32,))
+    if cube.dim() < 2:
+        raise ValueError("cube must have at least 2 dimensions (..., C)")
+    Cn = cube.shape[-1]
+    npix = cube.numel() // Cn
+    if calibration is not None:
+        calibration = _dev(calibration, "calibration", (torch.float32,))
+        if calibration.shape != cube.shape:
+            calibration = calibration.expand_as(cube).contiguous()
+    out = torch.empty(cube.shape[:-1], dtype=dtype, device=cube.device)
+    mk = MaxKey(cube.device) if (normalize or return_max) else None
+    with torch.cuda.device(cube.device):
+        check(lib().hipr_chansum(C.c_void_p(cube.data_ptr()),
+                                 C.c_void_p(calibration.data_ptr()) if calibration is not None else None,
+                                 npix, Cn, C.c_void_p(out.data_ptr()), _DT[dtype],
+                                 mk.ptr() if mk else None, _stream()), "channel_sum")
+        if normalize:
+            check(lib().hipr_normalize(C.c_void_p(out.data_ptr()), _DT[dtype], npix, mk.ptr(), _stream()),
+                  "normalize")
+    return (out, mk) if return_max else out
+
+
+def lne2d(image, flavour="F1", patch_size=11, phi_range=9, padded=False, maxkey=None):
+    """Score map ("local neighbourhood enhancement") of a 2-D image.
+
+    image: (H, W) when padded=False (border samples clamp to the edge, = np.pad(mode='edge')),
+    or the already padded (H+P-1, W+P-1) image when padded=True.  maxkey: optional MaxKey from
+    channel_sum(normalize=False, return_max=True); samples are divided by the max on load."""
+    image = _dev(image, "image")
+    if image.dim() != 2:
+        raise ValueError("image must be 2-D, got %d-D" % image.dim())
+    tab = tables.line_table_2d(patch_size, phi_range)
+    P = tab.shape[1]
+    Hs, Ws = image.shape
+    H, W = (Hs - P + 1, Ws - P + 1) if padded else (Hs, Ws)
+    if H < 1 or W < 1:
+        raise ValueError("image smaller than the patch")
+    out = torch.empty((H, W), dtype=image.dtype, device=image.device)
+    with torch.cuda.device(image.device):
+        check(lib().hipr_lne2d(C.c_void_p(image.data_ptr()), Hs, Ws, Ws, int(bool(padded)), _DT[image.dtype], P,
+                               tab.shape[0], _tab_ptr(tab), _flavour(flavour),
+                               maxkey.ptr() if maxkey is not None else None, C.c_void_p(out.data_ptr()),
+                               _stream()), "lne2d")
+    return out
+
+
+def image_range(image):
+    """MaxKey (max and min keys) of any float image, for lne2d_fixed."""
+    image = _dev(image, "image")
+    mk = MaxKey(image.device)
+    with torch.cuda.device(image.device):
+        check(lib().hipr_image_range(C.c_void_p(image.data_ptr()), _DT[image.dtype], image.numel(), mk.ptr(),
+                                     _stream()), "image_range")
+    return mk
+
+
+def lne2d_fixed(image, flavour="F1", patch_size=11, phi_range=9, padded=False, range_keys=None):
+    """lne2d on a 31-bit fixed-point copy of the image (csrc/lne2d_q.cu): min, max and differences
+    along each line are exact, so a float64 image keeps its precision at float32 speed.  The
+    implied normalisation is image / max(image).  (11, 9) only; float32 score out."""
+    image = _dev(image, "image")
+    if image.dim() != 2:
+        raise ValueError("image must be 2-D, got %d-D" % image.dim())
+    tab = tables.line_table_2d(patch_size, phi_range)
+    if tab.shape[:2] != (9, 11):
+        raise ValueError("the fixed-point stencil exists for patch_size=11, phi_range=9 only; use lne2d")
+    if range_keys is None:
+        range_keys = image_range(image)
+    Hs, Ws = image.shape
+    H, W = (Hs - 10, Ws - 10) if padded else (Hs, Ws)
+    if H < 1 or W < 1:
+        raise ValueError("image smaller than the patch")
+    out = torch.empty((H, W), dtype=torch.float32, device=image.device)
+    with torch.cuda.device(image.device):
+        check(lib().hipr_lne2d_q(C.c_void_p(image.data_ptr()), Hs, Ws, Ws, int(bool(padded)), _DT[image.dtype], 11, 9,
+                                 _tab_ptr(tab), _flavour(flavour), range_keys.ptr(), C.c_void_p(out.data_ptr()),
+                                 _stream()), "lne2d_fixed")
+    return out
+
+
+def neighbor2d_score(cube, flavour="F1", calibration=None, patch_size=11, phi_range=9, dtype=None,
+                     return_sum=False):
+    """cube (H, W, C) or (N, H, W, C) float32 -> score map(s) (H, W) / (N, H, W).
+
+    channel sum -> /max -> edge pad -> line profiles -> epilogue, FOV by FOV (each FOV has its
+    own max).  dtype=None (default): float64 channel sums feed the fixed-point stencil
+    (lne2d_fixed; float32 score).  dtype=torch.float32 / float64: the sum image is stored in that
+    type and the floating-point stencil of that type runs, dividing by the max on load."""
+    cube = _dev(cube, "cube", (torch.float32,))
+    if cube.dim() == 4:
+        res = [neighbor2d_score(c, flavour, None if calibration is None else calibration, patch_size, phi_range,
+                                dtype, return_sum) for c in cube]
+        if return_sum:
+            return torch.stack([r[0] for r in res]), torch.stack([r[1] for r in res])
+        return torch.stack(res)
+    if cube.dim() != 3:
+        raise ValueError("cube must be (H, W, C) or (N, H, W, C)")
+    fixed = dtype is None and tables.line_table_2d(patch_size, phi_range).shape[:2] == (9, 11)
+    if dtype is None:
+        dtype = torch.float64
+    s, mk = channel_sum(cube, calibration, normalize=False, dtype=dtype, return_max=True)
+    if fixed:
+        score = lne2d_fixed(s, flavour, patch_size, phi_range, padded=False, range_keys=mk)
+    else:
+        score = lne2d(s, flavour, patch_size, phi_range, padded=False, maxkey=mk)
+    if return_sum:
+        with torch.cuda.device(cube.device):
+            check(lib().hipr_normalize(C.c_void_p(s.data_ptr()), _DT[dtype], s.numel(), mk.ptr(), _stream()),
+                  "normalize")
+        return score, s
+    return score
+
+
+def line_profile_2d(image_padded, patch_size, phi_range):
+    """Literal gather: (Hp, Wp) -> (Hp-P+1, Wp-P+1, phi_range, P), same dtype."""
+    image_padded = _dev(image_padded, "image_padded")
+    if image_padded.dim() != 2:
+        raise ValueError("Buffer has wrong number of dimensions (expected 2, got %d)" % image_padded.dim())
+    tab = tables.line_table_2d(patch_size, phi_range)
+    R, P = tab.shape[0], tab.shape[1]
+    Hp, Wp = image_padded.shape
+    if Hp < P or Wp < P:
+        raise ValueError("image smaller than the patch")
+    out = torch.empty((Hp - P + 1, Wp - P + 1, R, P), dtype=image_padded.dtype, device=image_padded.device)
+    with torch.cuda.device(image_padded.device):
+        check(lib().hipr_line_profile_2d(C.c_void_p(image_padded.data_ptr()), Hp, Wp, _DT[image_padded.dtype], P, R,
+                                         _tab_ptr(tab), C.c_void_p(out.data_ptr()), _stream()), "line_profile_2d")
+    return out
+
+
+def _vol(volume, name):
+    volume = _dev(volume, name)
+    if volume.dim() != 3:
+        raise ValueError("Buffer has wrong number of dimensions (expected 3, got %d)" % volume.dim())
+    return volume
+
+
+def line_profile_3d(volume_padded, patch_size, theta_range, phi_range):
+    """Literal 5-D gather: (Xp, Yp, Zp) -> (X, Y, Z, (theta_range-1)*phi_range, P)."""
+    v = _vol(volume_padded, "image_padded")
+    tab = tables.line_table_3d(patch_size, theta_range, phi_range)
+    T, P = tab.shape[0], tab.shape[1]
+    Xp, Yp, Zp = v.shape
+    if min(Xp, Yp, Zp) < P:
+        raise ValueError("volume smaller than the patch")
+    out = torch.empty((Xp - P + 1, Yp - P + 1, Zp - P + 1, T, P), dtype=v.dtype, device=v.device)
+    with torch.cuda.device(v.device):
+        check(lib().hipr_line_profile_3d(C.c_void_p(v.data_ptr()), Xp, Yp, Zp, _DT[v.dtype], P, T, _tab_ptr(tab),
+                                         C.c_void_p(out.data_ptr()), _stream()), "line_profile_3d")
+    return out
+
+
+def lne3d_dirs(volume, patch_size=11, theta_range=9, phi_range=9, padded=True, maxkey=None):
+    """line_profile_memory_efficient_v2: per-direction relative centre value, (X, Y, Z, T)."""
+    v = _vol(volume, "image_padded")
+    tab = tables.line_table_3d(patch_size, theta_range, phi_range)
+    T, P = tab.shape[0], tab.shape[1]
+    Xs, Ys, Zs = v.shape
+    dims = [d - P + 1 for d in v.shape] if padded else list(v.shape)
+    if min(dims) < 1:
+        raise ValueError("volume smaller than the patch")
+    out = torch.empty(dims + [T], dtype=v.dtype, device=v.device)
+    with torch.cuda.device(v.device):
+        check(lib().hipr_lne3d_dirs(C.c_void_p(v.data_ptr()), Xs, Ys, Zs, int(bool(padded)), _DT[v.dtype], P, T,
+                                    _tab_ptr(tab), maxkey.ptr() if maxkey is not None else None,
+                                    C.c_void_p(out.data_ptr()), _stream()), "lne3d_dirs")
+    return out
+
+
+def lne3d(volume, flavour="F2", patch_size=11, theta_range=9, phi_range=9, padded=False, maxkey=None):
+    """3-D score map (X, Y, Z).  flavour 'F2' / 'F3' / 'ME2', or 'V3' (needs padded=True)."""
+    v = _vol(volume, "volume")
+    if flavour == "V3":
+        tab = tables.line_table_3d_v3(patch_size, theta_range, phi_range)
+    else:
+        tab = tables.line_table_3d(patch_size, theta_range, phi_range)
+    T, P = tab.shape[0], tab.shape[1]
+    Xs, Ys, Zs = v.shape
+    dims = [d - P + 1 for d in v.shape] if padded else list(v.shape)
+    if min(dims) < 1:
+        raise ValueError("volume smaller than the patch")
+    out = torch.empty(dims, dtype=v.dtype, device=v.device)
+    with torch.cuda.device(v.device):
+        check(lib().hipr_lne3d(C.c_void_p(v.data_ptr()), Xs, Ys, Zs, int(bool(padded)), _DT[v.dtype], P, T,
+                               _tab_ptr(tab), _flavour(flavour), maxkey.ptr() if maxkey is not None else None,
+                               C.c_void_p(out.data_ptr()), _stream()), "lne3d")
+    return out
+
+
+def neighbor3d_score(cube, flavour="ME2", patch_size=11, theta_range=9, phi_range=9, dtype=torch.float32):
+    """cube (X, Y, Z, C) float32 -> score volume (X, Y, Z): channel sum -> /max -> edge pad ->
+    3-D line profiles -> epilogue (bio/...analysis.py:807-817 for 'ME2')."""
+    cube = _dev(cube, "cube", (torch.float32,))
+    if cube.dim() != 4:
+        raise ValueError("cube must be (X, Y, Z, C)")
+    s, mk = channel_sum(cube, None, normalize=False, dtype=dtype, return_max=True)
+    return lne3d(s, flavour, patch_size, theta_range, phi_range, padded=False, maxkey=mk)
+
+
+# ---------------------------------------------------------------------------------------------
+# per-cell spectra
+# ---------------------------------------------------------------------------------------------
+
+def label_max(labels):
+    labels = _dev(labels, "labels", (torch.int32, torch.int64))
+    out = torch.empty(1, dtype=torch.int64, device=labels.device)
+    with torch.cuda.device(labels.device):
+        check(lib().hipr_label_max(C.c_void_p(labels.data_ptr()), labels.element_size(), labels.numel(),
+                                   C.c_void_p(out.data_ptr()), _stream()), "label_max")
+    return out
+
+
+def cell_spectra_accumulate(cube, labels, max_label, sums=None, counts=None):
+    """Adds this (slab of a) label image's per-label channel sums and pixel counts into
+    sums (max_label+1, C) float64 / counts (max_label+1) int32 (allocated zeroed if None)."""
+    cube = _dev(cube, "cube", (torch.float32,))
+    labels = _dev(labels, "labels", (torch.int32, torch.int64))
+    Cn = cube.shape[-1]
+    npix = labels.numel()
+    if cube.numel() != npix * Cn:
+        raise ValueError("cube %s and labels %s do not match" % (tuple(cube.shape), tuple(labels.shape)))
+    max_label = int(max_label)
+    if sums is None:
+        sums = torch.zeros((max_label + 1, Cn), dtype=torch.float64, device=cube.device)
+    if counts is None:
+        counts = torch.zeros(max_label + 1, dtype=torch.int32, device=cube.device)
+    with torch.cuda.device(cube.device):
+        check(lib().hipr_cell_spectra_accumulate(C.c_void_p(cube.data_ptr()), C.c_void_p(labels.data_ptr()),
+                                                 labels.element_size(), npix, Cn, max_label,
+                                                 C.c_void_p(sums.data_ptr()), C.c_void_p(counts.data_ptr()), None,
+                                                 _stream()), "cell_spectra_accumulate")
+    return sums, counts
+
+
+def cell_spectra_finalize(sums, counts):
+    """-> (labels int64 (n,), area int64 (n,), avgint float64 (n, C), avgint_norm float64 (n, C)),
+    rows in ascending order of the labels present.  Synchronises once to learn n."""
+    max_label, Cn = sums.shape[0] - 1, sums.shape[1]
+    dev = sums.device
+    cap = max(max_label, 1)
+    n_cells = torch.zeros(1, dtype=torch.int32, device=dev)
+    labels = torch.empty(cap, dtype=torch.int64, device=dev)
+    area = torch.empty(cap, dtype=torch.int64, device=dev)
+    avg = torch.empty((cap, Cn), dtype=torch.float64, device=dev)
+    norm = torch.empty((cap, Cn), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        check(lib().hipr_cell_spectra_finalize(C.c_void_p(sums.data_ptr()), C.c_void_p(counts.data_ptr()), max_label,
+                                               Cn, C.c_void_p(n_cells.data_ptr()), C.c_void_p(labels.data_ptr()),
+                                               C.c_void_p(area.data_ptr()), C.c_void_p(avg.data_ptr()),
+                                               C.c_void_p(norm.data_ptr()), _stream()), "cell_spectra_finalize")
+    n = int(n_cells.item())
+    return labels[:n], area[:n], avg[:n], norm[:n]
+
+
+def cell_spectra(cube, labels, max_label=None):
+    """regionprops-equivalent per-cell mean spectra of cube (..., C) over the label image."""
+    if max_label is None:
+        max_label = int(label_max(labels).item())
+    sums, counts = cell_spectra_accumulate(cube, labels, max_label)
+    return cell_spectra_finalize(sums, counts)
+
+
+# ---------------------------------------------------------------------------------------------
+# host-buffer (numpy) entry points: copies happen inside the library
+# ---------------------------------------------------------------------------------------------
+
+def pinned_empty(shape, dtype=np.float32):
+    """numpy array backed by page-locked memory from hipr_host_alloc (freed with the array)."""
+    dtype = np.dtype(dtype)
+    nbytes = int(np.prod(shape)) * dtype.itemsize
+    p = C.c_void_p()
+    check(lib().hipr_host_alloc(C.byref(p), max(nbytes, 1)), "host_alloc")
+
+    class _Owner:
+        def __init__(self, ptr):
+            self.ptr = ptr
+
+        def __del__(self):
+            try:
+                lib().hipr_host_free(self.ptr)
+            except Exception:
+                pass
+
+    buf = (C.c_char * max(nbytes, 1)).from_address(p.value)
+    buf._hipr_owner = _Owner(p)
+    return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+
+def neighbor2d_score_host(cube, flavour="F1", patch_size=11, phi_range=9, return_sum=False, out=None):
+    """numpy (H, W, C) float32 -> numpy (H, W) float32 score map, through hipr_neighbor2d_host."""
+    cube = np.ascontiguousarray(cube)
+    if cube.dtype != np.float32:
+        raise TypeError("cube must be float32, got %s" % cube.dtype)
+    if cube.ndim != 3:
+        raise ValueError("cube must be (H, W, C)")
+    H, W, Cn = cube.shape
+    tab = tables.line_table_2d(patch_size, phi_range)
+    score = out if out is not None else np.empty((H, W), dtype=np.float32)
+    s = np.empty((H, W), dtype=np.float32) if return_sum else None
+    check(lib().hipr_neighbor2d_host(cube.ctypes.data_as(C.c_void_p), H, W, Cn, tab.shape[1], tab.shape[0],
+                                     _tab_ptr(tab), _flavour(flavour), score.ctypes.data_as(C.c_void_p),
+                                     s.ctypes.data_as(C.c_void_p) if return_sum else None), "neighbor2d_host")
+    return (score, s) if return_sum else score
+
+
+def cell_spectra_host(cube, labels):
+    """numpy cube (..., C) float32 + integer label image -> (labels, area, avgint, avgint_norm)."""
+    cube = np.ascontiguousarray(cube)
+    labels = np.ascontiguousarray(labels)
+    if cube.dtype != np.float32:
+        raise TypeError("cube must be float32, got %s" % cube.dtype)
+    if labels.dtype not in (np.int32, np.int64):
+        raise TypeError("labels must be int32 or int64, got %s" % labels.dtype)
+    Cn = cube.shape[-1]
+    npix = labels.size
+    if cube.size != npix * Cn:
+        raise ValueError("cube and labels do not match")
+    cap = 1024
+    while True:
+        n = C.c_int64(0)
+        lab = np.empty(cap, np.int64)
+        area = np.empty(cap, np.int64)
+        avg = np.empty((cap, Cn), np.float64)
+        norm = np.empty((cap, Cn), np.float64)
+        code = lib().hipr_cell_spectra_host(cube.ctypes.data_as(C.c_void_p), labels.ctypes.data_as(C.c_void_p),
+                                            labels.itemsize, npix, Cn, cap, C.byref(n),
+                                            lab.ctypes.data_as(C.c_void_p), area.ctypes.data_as(C.c_void_p),
+                                            avg.ctypes.data_as(C.c_void_p), norm.ctypes.data_as(C.c_void_p))
+        if code == -7 and n.value > cap:
+            cap = int(n.value)
+            continue
+        check(code, "cell_spectra_host")
+        k = int(n.value)
+        return lab[:k], area[:k], avg[:k], norm[:k]

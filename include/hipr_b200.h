@@ -1,0 +1,196 @@
+/*
+ * hipr_b200.h -- C ABI of libhipr_b200.so, the B200 (sm_100a) implementation of the HiPR-FISH
+ * spectral-segmentation front end.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch/numpy types.  Every entry
+ * point names the reference code it replaces (paths relative to the reference repository;
+ * eco/ = hiprfish-image-analysis-ecoli, bio/ = hiprfish-image-analysis-biofilm,
+ * syn/ = hiprfish-image-analysis-synthetic-community).  INTEGRATION.md shows the ctypes
+ * binding a reference maintainer adds.
+ *
+ * Conventions
+ *  - All arrays are C-contiguous, channel (or line sample) fastest, exactly as the reference's
+ *    numpy arrays are.  "dev" pointers are device pointers, "host" pointers host memory.
+ *  - dtype codes: HIPR_F32 = 0 (float), HIPR_F64 = 1 (double).
+ *  - Every function returns 0 on success, a negative HIPR_E* code for a rejected argument, or
+ *    a positive cudaError_t value.  hipr_error_string() describes either.
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Device entry
+ *    points only enqueue work; they never synchronise.
+ *  - Line tables are passed as HOST int32 arrays in patch coordinates (0 .. patch_size-1),
+ *    shape (n_dirs, patch_size, ndim), as built by eco/neighbor2d.pyx:32-55 or
+ *    bio/neighbor.pyx:141-170; the library never recomputes them (they depend on libm
+ *    rounding).
+ */
+#ifndef HIPR_B200_H
+#define HIPR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HIPR_ABI_VERSION 1
+
+#define HIPR_F32 0
+#define HIPR_F64 1
+
+/* epilogue flavours */
+#define HIPR_FLAVOUR_F1  1  /* syn/..._measurement.py:111-124 */
+#define HIPR_FLAVOUR_F2  2  /* bio/..._analysis.py:905-917 */
+#define HIPR_FLAVOUR_F3  3  /* bio/..._analysis.py:1114-1125 */
+#define HIPR_FLAVOUR_ME2 4  /* bio/neighbor.pyx:256-262 + bio/..._analysis.py:812-817 */
+#define HIPR_FLAVOUR_V3  5  /* bio/neighbor.pyx:335-348 */
+
+#define HIPR_OK            0
+#define HIPR_E_ARG        -1  /* null pointer / non-positive size */
+#define HIPR_E_DTYPE      -2
+#define HIPR_E_PATCH      -3  /* patch_size even, < 3 or too large; image smaller than patch */
+#define HIPR_E_TABLE      -4  /* table entry outside the patch / table too large */
+#define HIPR_E_FLAVOUR    -5
+#define HIPR_E_ALIGN      -6
+#define HIPR_E_RANGE      -7  /* size overflows the kernel's index type */
+#define HIPR_E_NODEVICE   -8
+
+#define HIPR_MAX_PATCH     31
+#define HIPR_MAX_TABLE     960   /* n_dirs * patch_size, fits the kernel parameter bank */
+#define HIPR_MAX_DIRS      128
+
+int         hipr_abi_version(void);
+const char *hipr_error_string(int code);
+/* number of kernels this library has launched in the calling process (for bench.py) */
+int64_t     hipr_launch_count(void);
+/* multiprocessor count of the current device, or a negative error */
+int         hipr_sm_count(void);
+
+/* ---- prologue: channel sum (+ global max) -------------------------------------------------
+ * Replaces `np.sum(image_channel, axis=2)` and the np.max that follows it,
+ * syn/..._measurement.py:105-106 (bio/..._analysis.py:347-348, 451-452, 808-809).
+ *   cube_dev   (npix, C) float32
+ *   calib_dev  NULL, or (npix, C) float32 flat-field divisor (syn/..._measurement.py:104)
+ *   sum_dev    (npix) of sum_dtype; channel sums are accumulated in float64 either way
+ *   maxkey_dev NULL, or TWO uint64: [0] receives an order-preserving key of max(sum), [1] of
+ *              min(sum) (decode with hipr_maxkey_decode; consumed by hipr_normalize,
+ *              hipr_lne2d, hipr_lne2d_q); both are reset by this call
+ */
+int hipr_chansum(const float *cube_dev, const float *calib_dev, int64_t npix, int C,
+                 void *sum_dev, int sum_dtype, uint64_t *maxkey_dev, void *stream);
+
+/* global min / max of any image as keys: range_dev[0] = max key, range_dev[1] = min key */
+int hipr_image_range(const void *image_dev, int dtype, int64_t n, uint64_t *range_dev, void *stream);
+/* out_dev[i] = (float)(sum_dev[i] / max), out of place from a float64 sum image
+ * (maxkey_dev NULL: plain float64 -> float32 cast) */
+int hipr_normalize_cast(const double *sum_dev, int64_t npix, const uint64_t *maxkey_dev, float *out_dev,
+                        void *stream);
+
+/* sum_dev[i] /= max   (syn/..._measurement.py:106).  maxkey_dev from hipr_chansum. */
+int hipr_normalize(void *sum_dev, int sum_dtype, int64_t npix, const uint64_t *maxkey_dev,
+                   void *stream);
+/* decode the key into a double on the device (for callers that want the scalar) */
+int hipr_maxkey_decode(const uint64_t *maxkey_dev, double *max_dev, void *stream);
+
+/* ---- 2-D literal stencil ------------------------------------------------------------------
+ * Replaces line_profile_2d_v2(image_padded, patch_size, phi_range), eco/neighbor2d.pyx:8-64:
+ *   out[i, j, t, li] = image_padded[i + table[t, li, 0], j + table[t, li, 1]]
+ *   image_padded_dev (Hp, Wp) of dtype;  out_dev (Hp-P+1, Wp-P+1, n_dirs, P) of dtype
+ */
+int hipr_line_profile_2d(const void *image_padded_dev, int Hp, int Wp, int dtype,
+                         int patch_size, int n_dirs, const int32_t *table_host,
+                         void *out_dev, void *stream);
+
+/* ---- 2-D fused stencil + epilogue ("local neighbourhood enhancement") ---------------------
+ * Replaces line_profile_2d_v2 (eco/neighbor2d.pyx:56-63) + the numpy epilogue of `flavour`
+ * (F1 syn/..._measurement.py:111-124, F2 bio/..._analysis.py:671-683, F3 :1114-1125) and,
+ * when padded == 0, the edge pad before it (syn/..._measurement.py:109).
+ *   image_dev  (Hs, Ws) of dtype, row pitch `ld` elements.  padded != 0: it is the padded
+ *              image and the output is (Hs-P+1, Ws-P+1); padded == 0: it is the unpadded
+ *              image, border samples clamp to the edge, output is (Hs, Ws)
+ *   maxkey_dev NULL, or the key from hipr_chansum: samples are divided by the max on load
+ *   out_dev    (H, W) of dtype
+ */
+int hipr_lne2d(const void *image_dev, int Hs, int Ws, int64_t ld, int padded, int dtype,
+               int patch_size, int n_dirs, const int32_t *table_host, int flavour,
+               const uint64_t *maxkey_dev, void *out_dev, void *stream);
+
+/* Same operation on a 31-bit fixed-point copy of the image (exact min / max / differences; see
+ * csrc/lne2d_q.cu).  This is what the cube -> score pipeline uses: image_dev is the float64 (or
+ * float32) channel-sum image, range_dev the two keys from hipr_chansum / hipr_image_range; the
+ * division by max is implied (the score is invariant to it; F3's epsilon is rescaled).
+ * patch_size must be 11 and n_dirs 9 (HIPR_E_TABLE otherwise: use hipr_lne2d).  out is float32.
+ */
+int hipr_lne2d_q(const void *image_dev, int Hs, int Ws, int64_t ld, int padded, int dtype,
+                 int patch_size, int n_dirs, const int32_t *table_host, int flavour,
+                 const uint64_t *range_dev, float *out_dev, void *stream);
+
+/* ---- 3-D stencils -------------------------------------------------------------------------
+ * hipr_line_profile_3d replaces line_profile_v2, bio/neighbor.pyx:115-181
+ *   out (X, Y, Z, n_dirs, P).
+ * hipr_lne3d_dirs replaces line_profile_memory_efficient_v2, bio/neighbor.pyx:186-263
+ *   out (X, Y, Z, n_dirs): (centre - min) / max(max - min, 1e-8) per direction.
+ * hipr_lne3d replaces the stencil + epilogue: F2 (bio/..._analysis.py:904-917), F3
+ *   (:1112-1125), ME2 (:811-817), V3 = line_profile_memory_efficient_v3
+ *   (bio/neighbor.pyx:268-349; pass the v3 table, reads use flat addressing).
+ * volume_dev is the PADDED volume (Xp, Yp, Zp) unless padded == 0 (edge clamp, as 2-D).
+ */
+int hipr_line_profile_3d(const void *volume_padded_dev, int Xp, int Yp, int Zp, int dtype,
+                         int patch_size, int n_dirs, const int32_t *table_host,
+                         void *out_dev, void *stream);
+int hipr_lne3d_dirs(const void *volume_dev, int Xs, int Ys, int Zs, int padded, int dtype,
+                    int patch_size, int n_dirs, const int32_t *table_host,
+                    const uint64_t *maxkey_dev, void *out_dev, void *stream);
+int hipr_lne3d(const void *volume_dev, int Xs, int Ys, int Zs, int padded, int dtype,
+               int patch_size, int n_dirs, const int32_t *table_host, int flavour,
+               const uint64_t *maxkey_dev, void *out_dev, void *stream);
+
+/* ---- per-cell mean spectra ----------------------------------------------------------------
+ * Replaces the regionprops loop, syn/..._measurement.py:167-172 (eco/...:151-157,
+ * ref/...:177-183, bio/..._analysis.py:1214-1220, 1364-1369).
+ * hipr_label_max:   max label (int64, >= 0) of a label image; label_bytes is 4 or 8.
+ * hipr_cell_spectra_accumulate:
+ *   cube_dev (npix, C) float32; labels_dev (npix) int32/int64, <= 0 = background;
+ *   sums_dev (max_label+1, C) float64 and counts_dev (max_label+1) int32 are ADDED to (zero
+ *   them first, or keep accumulating slabs / all-reduce them across ranks); labels above
+ *   max_label are counted in *overflow_dev (int32, may be NULL).
+ * hipr_cell_spectra_finalize:
+ *   compacts to the labels present, ascending (regionprops order):
+ *   n_cells_dev (1) int32; labels_out (max_label) int64; area_out (max_label) int64;
+ *   avgint_out, avgint_norm_out (max_label, C) float64 -- the first n_cells rows are valid;
+ *   avgint_norm = avgint / max(avgint, axis=1) (syn/..._measurement.py:172).
+ */
+int hipr_label_max(const void *labels_dev, int label_bytes, int64_t npix, int64_t *max_dev,
+                   void *stream);
+int hipr_cell_spectra_accumulate(const float *cube_dev, const void *labels_dev,
+                                 int label_bytes, int64_t npix, int C, int64_t max_label,
+                                 double *sums_dev, int32_t *counts_dev, int32_t *overflow_dev,
+                                 void *stream);
+int hipr_cell_spectra_finalize(const double *sums_dev, const int32_t *counts_dev,
+                               int64_t max_label, int C, int32_t *n_cells_dev,
+                               int64_t *labels_out, int64_t *area_out, double *avgint_out,
+                               double *avgint_norm_out, void *stream);
+
+/* ---- host-buffer entry points (what a numpy caller binds; copies are inside) --------------
+ * hipr_neighbor2d_host: cube_host (H, W, C) float32 -> score_host (H, W) float32:
+ *   channel sum -> /max -> edge pad -> line profiles -> epilogue `flavour`, i.e.
+ *   syn/..._measurement.py:105-124 without the skimage denoise (as bio/...:807-817 does).
+ *   sum_host may be NULL or receives the (H, W) float32 normalised sum image.
+ *   The cube is streamed to the device in row bands overlapped with the channel sum.
+ *   Pinned host memory (hipr_host_alloc) gives full PCIe rate; pageable memory works.
+ * hipr_cell_spectra_host: cube_host (npix, C) float32, labels_host (npix) int32/int64 ->
+ *   *n_cells, labels_out/area_out (capacity) int64, avgint/avgint_norm (capacity, C) float64;
+ *   returns HIPR_E_RANGE if capacity < number of cells.
+ */
+int hipr_neighbor2d_host(const float *cube_host, int H, int W, int C, int patch_size,
+                         int n_dirs, const int32_t *table_host, int flavour,
+                         float *score_host, float *sum_host);
+int hipr_cell_spectra_host(const float *cube_host, const void *labels_host, int label_bytes,
+                           int64_t npix, int C, int64_t capacity, int64_t *n_cells,
+                           int64_t *labels_out, int64_t *area_out, double *avgint_out,
+                           double *avgint_norm_out);
+int hipr_host_alloc(void **ptr, int64_t bytes);   /* page-locked host memory */
+int hipr_host_free(void *ptr);
+int hipr_host_release_workspace(void);            /* frees cached device buffers/streams */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HIPR_B200_H */

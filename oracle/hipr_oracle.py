@@ -1,0 +1,350 @@
+"""CPU oracle for the HiPR-FISH spectral-segmentation front end.  TEST INFRASTRUCTURE ONLY.
+
+This module is a numpy restatement of the reference algorithm; it is the checker, never the
+product.  Only tests/, __graft_entry__.smoke() and bench.py's CPU legs import it.  The product
+(hiprfish-image-analysis_b200/) never does and has no CPU fallback.
+
+Parity status: PINNED.  The reference ships no tests or golden vectors, but
+its native stencils compile here unmodified (oracle/build_ref.py -> oracle/_ref/), and
+tests/test_oracle_vs_ref.py checks every function below against that compiled reference;
+tests/golden/ freezes vectors generated from it (tests/golden/make_golden.py) so the pin
+also holds on the GPU box where /root/reference is absent.  The per-cell reduction follows
+scikit-image's regionprops (third-party, NOT vendored in the reference, version not pinned
+anywhere in the reference; era skimage 0.14-0.15): for that one function parity is pinned only
+on its published definition (arithmetic mean over label==L pixels, ascending present labels)
+and cross-checked against scipy.ndimage.mean.
+
+Paths are relative to /root/reference:
+  eco/ = hiprfish-image-analysis-ecoli/        bio/ = hiprfish-image-analysis-biofilm/
+  syn/ = hiprfish-image-analysis-synthetic-community/
+"""
+import numpy as np
+
+# --------------------------------------------------------------------------------------------
+# Offset tables
+# --------------------------------------------------------------------------------------------
+
+def _fill_line(tab, col, steps, half):
+    """Fill tab[:, :, col] for one direction.
+
+    `steps` = the rounded end-point offsets of the half line (one per axis).  Follows
+    eco/neighbor2d.pyx:36-55 (2-D) and bio/neighbor.pyx:147-170 (3-D, same construction with a
+    third axis): the longest axis decides how many distinct samples the line has; shorter lines
+    are centred and their two end samples replicated.
+    """
+    P = tab.shape[0]
+    steps = np.asarray(steps, dtype=np.int64)
+    longest = steps[np.argmax(np.abs(steps))]
+    sgn = np.sign(steps)
+    n = int(2 * abs(longest) + 1)
+    first = int((P - n) / 2) if n < P else 0
+    for li in range(n):
+        for ax in range(len(steps)):
+            h = sgn[ax] * li * (2 * abs(steps[ax]) + 1) / n          # true division
+            tab[li + first, ax, col] = int(np.sign(h) * np.floor(np.abs(h)) + half - steps[ax])
+    if n < P:
+        for li in range(first):
+            tab[li, :, col] = tab[first, :, col]
+        for li in range(first):
+            tab[li + n + first, :, col] = tab[n + first - 1, :, col]
+
+
+def line_table_2d(patch_size, phi_range):
+    """(P, 2, R) int64 patch coordinates, eco/neighbor2d.pyx:32-55."""
+    half = int((patch_size - 1) / 2)
+    tab = np.zeros((patch_size, 2, phi_range), dtype=np.int64)
+    for phi in range(phi_range):
+        a = int(np.round(half * np.cos(phi * np.pi / phi_range)))
+        b = int(np.round(half * np.sin(phi * np.pi / phi_range)))
+        _fill_line(tab, phi, (a, b), half)
+    return tab
+
+
+def line_table_3d(patch_size, theta_range, phi_range):
+    """(P, 3, (theta_range-1)*phi_range) int64, bio/neighbor.pyx:141-170 (v2 and me_v2)."""
+    half = int((patch_size - 1) / 2)
+    tab = np.zeros((patch_size, 3, (theta_range - 1) * phi_range), dtype=np.int64)
+    for theta in range(1, theta_range):
+        for phi in range(phi_range):
+            col = (theta - 1) * phi_range + phi
+            st = np.sin(theta * np.pi / theta_range)
+            a = int(np.round(half * np.cos(phi * np.pi / phi_range) * st))
+            b = int(np.round(half * np.sin(phi * np.pi / phi_range) * st))
+            c = int(np.round(half * np.cos(theta * np.pi / theta_range)))
+            _fill_line(tab, col, (a, b, c), half)
+    return tab
+
+
+def line_table_3d_v3(patch_size, theta_range, phi_range):
+    """(P, 3, T) int64 table of line_profile_memory_efficient_v3, bio/neighbor.pyx:301-324.
+
+    Differs from line_table_3d: short lines use np.round of the signed fraction (:313-315);
+    full-length lines use np.floor of sign*li*(2*step+1)/n with the SIGNED step (:322-324).
+    """
+    half = int((patch_size - 1) / 2)
+    T = (theta_range - 1) * phi_range
+    tab = np.zeros((patch_size, 3, T), dtype=np.int64)
+    for theta in range(1, theta_range):
+        for phi in range(phi_range):
+            col = (theta - 1) * phi_range + phi
+            st = np.sin(theta * np.pi / theta_range)
+            steps = np.array([int(np.round(half * np.cos(phi * np.pi / phi_range) * st)),
+                              int(np.round(half * np.sin(phi * np.pi / phi_range) * st)),
+                              int(np.round(half * np.cos(theta * np.pi / theta_range)))], dtype=np.int64)
+            longest = steps[np.argmax(np.abs(steps))]
+            sgn = np.sign(steps)
+            n = int(2 * abs(longest) + 1)
+            if n < patch_size:
+                first = int((patch_size - n) / 2)
+                for li in range(n):
+                    for ax in range(3):
+                        tab[li + first, ax, col] = int(np.round(sgn[ax] * li * (2 * abs(steps[ax]) + 1) / n)
+                                                       + half - steps[ax])
+                for li in range(first):
+                    tab[li, :, col] = tab[first, :, col]
+                for li in range(first):
+                    tab[li + n + first, :, col] = tab[n + first - 1, :, col]
+            else:
+                for li in range(n):
+                    for ax in range(3):
+                        tab[li, ax, col] = int(np.floor(sgn[ax] * li * (2 * steps[ax] + 1) / n)
+                                               + half - steps[ax])
+    return tab
+
+
+# --------------------------------------------------------------------------------------------
+# Stencils (vectorised restatements of the native hot loops)
+# --------------------------------------------------------------------------------------------
+
+def line_profile_2d_v2(image_padded, patch_size, phi_range):
+    """eco/neighbor2d.pyx:8-64: lp[i,j,t,li] = image_padded[i+tab[li,0,t], j+tab[li,1,t]]."""
+    a = np.asarray(image_padded)
+    if a.dtype != np.float64:
+        raise ValueError("Buffer dtype mismatch, expected 'double' but got '%s'" % a.dtype)
+    if a.ndim != 2:
+        raise ValueError("Buffer has wrong number of dimensions (expected 2, got %d)" % a.ndim)
+    tab = line_table_2d(patch_size, phi_range)
+    H = a.shape[0] - (patch_size - 1)
+    W = a.shape[1] - (patch_size - 1)
+    out = np.zeros((H, W, phi_range, patch_size), dtype=np.float64)
+    for t in range(phi_range):
+        for li in range(patch_size):
+            di, dj = tab[li, 0, t], tab[li, 1, t]
+            out[:, :, t, li] = a[di:di + H, dj:dj + W]
+    return out
+
+
+def _gather3d(a, tab, patch_size):
+    X = a.shape[0] - (patch_size - 1)
+    Y = a.shape[1] - (patch_size - 1)
+    Z = a.shape[2] - (patch_size - 1)
+    T = tab.shape[2]
+    out = np.zeros((X, Y, Z, T, patch_size), dtype=np.float64)
+    for t in range(T):
+        for li in range(patch_size):
+            di, dj, dk = tab[li, :, t]
+            out[:, :, :, t, li] = a[di:di + X, dj:dj + Y, dk:dk + Z]
+    return out
+
+
+def _gather3d_flat(a, tab, patch_size):
+    """Gather for the v3 table, whose entries reach 18 for (11,9,9): the reference indexes an
+    11^3 memoryview slice with them, bounds checks off (bio/neighbor.pyx:265-267,328-334), i.e.
+    it reads image_padded's buffer at the flat address.  In-buffer addresses are reproduced
+    exactly; an address past the end of the buffer (undefined behaviour in the reference)
+    yields NaN here."""
+    a = np.ascontiguousarray(a)
+    Xp, Yp, Zp = a.shape
+    X, Y, Z = Xp - (patch_size - 1), Yp - (patch_size - 1), Zp - (patch_size - 1)
+    T = tab.shape[2]
+    flat = np.concatenate([a.reshape(-1), [np.nan]])
+    i, j, k = np.meshgrid(np.arange(X), np.arange(Y), np.arange(Z), indexing="ij")
+    out = np.zeros((X, Y, Z, T, patch_size), dtype=np.float64)
+    for t in range(T):
+        for li in range(patch_size):
+            di, dj, dk = tab[li, :, t]
+            idx = ((i + di) * Yp + (j + dj)) * Zp + (k + dk)
+            idx = np.where((idx >= 0) & (idx < a.size), idx, a.size)
+            out[:, :, :, t, li] = flat[idx]
+    return out
+
+
+def _check3d(a):
+    if a.dtype != np.float64:
+        raise ValueError("Buffer dtype mismatch, expected 'double' but got '%s'" % a.dtype)
+    if a.ndim != 3:
+        raise ValueError("Buffer has wrong number of dimensions (expected 3, got %d)" % a.ndim)
+
+
+def line_profile_v2(image_padded, patch_size, theta_range, phi_range):
+    """bio/neighbor.pyx:115-181: 5-D literal gather (X,Y,Z,T,P)."""
+    a = np.asarray(image_padded)
+    _check3d(a)
+    return _gather3d(a, line_table_3d(patch_size, theta_range, phi_range), patch_size)
+
+
+def line_profile_memory_efficient_v2(image_padded, patch_size, theta_range, phi_range):
+    """bio/neighbor.pyx:186-263: per direction (centre-min)/max(max-min,1e-8) -> (X,Y,Z,T)."""
+    a = np.asarray(image_padded)
+    _check3d(a)
+    lp = _gather3d(a, line_table_3d(patch_size, theta_range, phi_range), patch_size)
+    mn = lp.min(axis=4)
+    rng = np.maximum(lp.max(axis=4) - mn, 1e-8)
+    return (lp[..., int((patch_size - 1) / 2)] - mn) / rng
+
+
+def line_profile_memory_efficient_v3(image_padded, patch_size, theta_range, phi_range):
+    """bio/neighbor.pyx:268-349: v3 table, then avg*(p25-p75)/(p25+p75+1e-8) per voxel (:342-348)."""
+    a = np.asarray(image_padded)
+    _check3d(a)
+    lp = _gather3d_flat(a, line_table_3d_v3(patch_size, theta_range, phi_range), patch_size)
+    mn = lp.min(axis=4)
+    rng = np.maximum(lp.max(axis=4) - mn, 1e-8)
+    e = (lp[..., int((patch_size - 1) / 2)] - mn) / rng
+    T = e.shape[3]
+    avg = np.zeros(e.shape[:3])
+    for t in range(T):                       # sequential accumulation order of :343-345
+        avg += e[..., t]
+    avg /= T
+    uq = np.percentile(e, 25, axis=3)        # names swapped in the reference (:346-347)
+    lq = np.percentile(e, 75, axis=3)
+    return avg * (uq - lq) / (uq + lq + 1e-8)
+
+
+# --------------------------------------------------------------------------------------------
+# Prologue / epilogue (numpy blocks of the measurement scripts)
+# --------------------------------------------------------------------------------------------
+
+def prologue(cube, calibration=None, normalize=True, pad=5, sum_axes=None):
+    """syn/...measurement.py:102-109 without the skimage NLM denoise.
+
+    cube (..., C) -> channel sum over the last axis (or `sum_axes`, bio/...:451) -> /max ->
+    edge pad -> float64.  Returns (sum_image, padded_float64).
+    """
+    x = np.asarray(cube, dtype=np.float64)
+    if calibration is not None:
+        x = x / np.asarray(calibration, dtype=np.float64)
+    s = np.sum(x, axis=(x.ndim - 1) if sum_axes is None else sum_axes)
+    sn = s / np.max(s) if normalize else s
+    return s, np.pad(sn, pad, mode="edge").astype(np.float64)
+
+
+def _mean_quartiles(rnc, axis):
+    m = np.average(rnc, axis=axis)
+    with np.errstate(invalid="ignore"):
+        lq = np.percentile(rnc, 25, axis=axis)
+        uq = np.percentile(rnc, 75, axis=axis)
+    return m, lq, uq
+
+
+def epilogue_F1(lp):
+    """syn/...measurement.py:111-124 (= bio/...:353-366, 595-608).  lp (..., R, P) -> (...)."""
+    with np.errstate(invalid="ignore", divide="ignore"):
+        lp = np.nan_to_num(lp)
+        mn = np.min(lp, axis=-1)
+        mx = np.max(lp, axis=-1) - mn
+        rel = (lp - mn[..., None]) / mx[..., None]
+        rnc = rel[..., int((lp.shape[-1] - 1) / 2)]
+        m, lq, uq = _mean_quartiles(rnc, rnc.ndim - 1)
+        qcv = np.zeros(uq.shape)
+        pre = (uq - lq) / (uq + lq + 1e-8)
+        qcv[uq > 0] = pre[uq > 0]
+        return m * (1 - qcv)
+
+
+def epilogue_F2(lp):
+    """bio/...:905-917 (and :671-683, 728-740, 995-1007 in 2-D): nan_to_num on qcv, no epsilon."""
+    with np.errstate(invalid="ignore", divide="ignore"):
+        lp = np.nan_to_num(lp)
+        mn = np.min(lp, axis=-1)
+        mx = np.max(lp, axis=-1) - mn
+        rel = (lp - mn[..., None]) / mx[..., None]
+        rnc = rel[..., int((lp.shape[-1] - 1) / 2)]
+        return epilogue_F2_dirs(rnc)
+
+
+def epilogue_F2_dirs(rnc):
+    """bio/...:457-462 and :812-817: the F2 reduction applied to the me_v2 output (..., T)."""
+    with np.errstate(invalid="ignore", divide="ignore"):
+        m, lq, uq = _mean_quartiles(rnc, rnc.ndim - 1)
+        qcv = np.nan_to_num((uq - lq) / (uq + lq))
+        return m * (1 - qcv)
+
+
+def epilogue_F3(lp):
+    """bio/...:1114-1125: +1e-8 on the line range and on uq+lq, no nan_to_num."""
+    with np.errstate(invalid="ignore", divide="ignore"):
+        mn = np.min(lp, axis=-1)
+        mx = np.max(lp, axis=-1) - mn
+        rel = (lp - mn[..., None]) / (mx[..., None] + 1e-8)
+        rnc = rel[..., int((lp.shape[-1] - 1) / 2)]
+        m, lq, uq = _mean_quartiles(rnc, rnc.ndim - 1)
+        qcv = (uq - lq) / (uq + lq + 1e-8)
+        return m * (1 - qcv)
+
+
+EPILOGUES = {"F1": epilogue_F1, "F2": epilogue_F2, "F3": epilogue_F3}
+
+
+def lne2d(image, flavour="F1", patch_size=11, phi_range=9, lp_func=None):
+    """pad(5,'edge') -> line_profile_2d_v2 -> epilogue; image is the (normalised) sum image."""
+    half = int((patch_size - 1) / 2)
+    padded = np.pad(np.asarray(image, dtype=np.float64), half, mode="edge")
+    lp = (lp_func or line_profile_2d_v2)(padded, patch_size, phi_range)
+    return EPILOGUES[flavour](lp)
+
+
+def lne3d(volume, flavour="F2", patch_size=11, theta_range=9, phi_range=9, lp_func=None, me_func=None):
+    """3-D score map.  'F2'/'F3': line_profile_v2 + epilogue (bio/...:904-917, 1112-1125);
+    'ME2': line_profile_memory_efficient_v2 + F2 reduction (bio/...:811-817)."""
+    half = int((patch_size - 1) / 2)
+    padded = np.pad(np.asarray(volume, dtype=np.float64), half, mode="edge")
+    if flavour == "ME2":
+        e = (me_func or line_profile_memory_efficient_v2)(padded, patch_size, theta_range, phi_range)
+        return epilogue_F2_dirs(e)
+    lp = (lp_func or line_profile_v2)(padded, patch_size, theta_range, phi_range)
+    return EPILOGUES[flavour](lp)
+
+
+# --------------------------------------------------------------------------------------------
+# Per-cell mean spectra
+# --------------------------------------------------------------------------------------------
+
+def cell_spectra(seg, img):
+    """syn/...measurement.py:167-172 (= eco/...:151-157, ref/...:177-183, bio/...:1214-1220).
+
+    skimage.measure.regionprops(seg, intensity_image=img[..., k]).mean_intensity for every
+    channel: the float64 arithmetic mean of img over the pixels of each label, regions in
+    ascending order of the labels present, label 0 (background) and negative labels ignored.
+    Returns (labels int64 (n,), area int64 (n,), avgint float64 (n, C), avgint_norm (n, C)).
+    """
+    seg = np.asarray(seg)
+    img = np.asarray(img)
+    C = img.shape[-1]
+    flat = seg.reshape(-1).astype(np.int64)
+    vals = img.reshape(-1, C).astype(np.float64)
+    keep = flat > 0
+    flat, vals = flat[keep], vals[keep]
+    if flat.size == 0:
+        z = np.zeros((0, C))
+        return np.zeros(0, np.int64), np.zeros(0, np.int64), z, z.copy()
+    area_all = np.bincount(flat)
+    labels = np.nonzero(area_all)[0]
+    area = area_all[labels]
+    avg = np.empty((labels.size, C), dtype=np.float64)
+    for k in range(C):
+        avg[:, k] = np.bincount(flat, weights=vals[:, k], minlength=area_all.size)[labels] / area
+    with np.errstate(invalid="ignore", divide="ignore"):
+        norm = avg / np.max(avg, axis=1)[:, None]
+    return labels.astype(np.int64), area.astype(np.int64), avg, norm
+
+
+# --------------------------------------------------------------------------------------------
+# Whole 2-D path, as the reference runs it (used by bench.py's CPU legs)
+# --------------------------------------------------------------------------------------------
+
+def neighbor2d_score(cube, flavour="F1", calibration=None, lp_func=None):
+    """cube (H,W,C) -> image_final (H,W): prologue (no NLM) + stencil + epilogue."""
+    _, padded = prologue(cube, calibration=calibration)
+    lp = (lp_func or line_profile_2d_v2)(padded, 11, 9)
+    return EPILOGUES[flavour](lp)

@@ -1,0 +1,240 @@
+"""GPU parity, 2-D path: libhipr_b200 (through the C ABI) against the oracle on seeded inputs.
+Gates: literal gather bit-exact; score maps rtol 1e-5."""
+import numpy as np
+import pytest
+
+from conftest import smooth_image
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5          # north_star: similarity maps within 1e-5 relative
+ATOL_F32 = 2e-6      # float32 storage of a [0,1] score; float64 runs use ATOL_F64
+ATOL_F64 = 1e-12
+
+
+def _cuda(torch, a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.mark.parametrize("shape", [(11, 11), (12, 40), (37, 53), (64, 64), (75, 130)])
+@pytest.mark.parametrize("params", [(11, 9), (7, 5), (5, 3), (15, 12)])
+def test_line_profile_2d_bit_exact_f64(torch_cuda, oracle, shape, params):
+    import neighbor2d
+    P, R = params
+    rng = np.random.default_rng(1)
+    a = rng.random((shape[0] + P - 1, shape[1] + P - 1))
+    got = neighbor2d.line_profile_2d_v2(a, P, R)
+    want = oracle.line_profile_2d_v2(a, P, R)
+    assert got.dtype == np.float64 and got.shape == want.shape
+    assert np.array_equal(got, want)
+
+
+def test_line_profile_2d_vs_compiled_reference(torch_cuda, ref2d):
+    import neighbor2d
+    a = np.random.default_rng(2).random((138, 75))
+    assert np.array_equal(neighbor2d.line_profile_2d_v2(a, 11, 9), ref2d.line_profile_2d_v2(a, 11, 9))
+
+
+def test_line_profile_2d_f32_device(torch_cuda, oracle):
+    import hipr_b200
+    a = np.random.default_rng(3).random((70, 91)).astype(np.float32)
+    got = hipr_b200.line_profile_2d(_cuda(torch_cuda, a), 11, 9).cpu().numpy()
+    want = oracle.line_profile_2d_v2(a.astype(np.float64), 11, 9).astype(np.float32)
+    assert np.array_equal(got, want)
+
+
+def test_line_profile_2d_noncontiguous_and_special_values(torch_cuda, oracle):
+    import neighbor2d
+    a = np.random.default_rng(4).random((60, 90))[::2, ::3]          # strided view, as a memoryview accepts
+    a = a.copy(); a[3, 4] = np.nan; a[7, 7] = np.inf; a[9, 1] = -0.0
+    view = np.asfortranarray(a)
+    got = neighbor2d.line_profile_2d_v2(view, 11, 9)
+    want = oracle.line_profile_2d_v2(np.ascontiguousarray(a), 11, 9)
+    assert np.array_equal(got, want, equal_nan=True)
+    assert np.array_equal(np.signbit(got), np.signbit(want))
+
+
+@pytest.mark.parametrize("flavour", ["F1", "F2", "F3"])
+@pytest.mark.parametrize("shape", [(1, 1), (5, 7), (32, 32), (33, 65), (97, 130)])
+def test_lne2d_f64(torch_cuda, oracle, flavour, shape):
+    import hipr_b200
+    img = smooth_image(shape, 5).astype(np.float64)
+    got = hipr_b200.lne2d(_cuda(torch_cuda, img), flavour).cpu().numpy()
+    want = oracle.lne2d(img, flavour)
+    np.testing.assert_allclose(got, want, rtol=RTOL, atol=ATOL_F64, equal_nan=True)
+
+
+@pytest.mark.parametrize("flavour", ["F1", "F2", "F3"])
+def test_lne2d_f32(torch_cuda, oracle, flavour):
+    import hipr_b200
+    img = smooth_image((150, 201), 6)
+    got = hipr_b200.lne2d(_cuda(torch_cuda, img), flavour).cpu().numpy()
+    want = oracle.lne2d(img.astype(np.float64), flavour)
+    assert got.dtype == np.float32
+    np.testing.assert_allclose(got, want, rtol=RTOL, atol=ATOL_F32)
+
+
+def test_lne2d_padded_equals_unpadded(torch_cuda):
+    import hipr_b200
+    img = smooth_image((80, 90), 7)
+    a = hipr_b200.lne2d(_cuda(torch_cuda, img), "F1").cpu().numpy()
+    b = hipr_b200.lne2d(_cuda(torch_cuda, np.pad(img, 5, mode="edge")), "F1", padded=True).cpu().numpy()
+    assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("params", [(7, 5), (5, 3), (15, 12), (11, 4), (9, 16)])
+@pytest.mark.parametrize("flavour", ["F1", "F2", "F3"])
+def test_lne2d_generic_parameters(torch_cuda, oracle, params, flavour):
+    import hipr_b200
+    P, R = params
+    img = smooth_image((41, 57), 8).astype(np.float64)
+    got = hipr_b200.lne2d(_cuda(torch_cuda, img), flavour, P, R).cpu().numpy()
+    want = oracle.lne2d(img, flavour, P, R)
+    np.testing.assert_allclose(got, want, rtol=RTOL, atol=ATOL_F64, equal_nan=True)
+
+
+@pytest.mark.parametrize("flavour", ["F1", "F2", "F3"])
+def test_lne2d_flat_and_nan_inputs(torch_cuda, oracle, flavour):
+    """Degenerate lines: flat regions give 0/0 = NaN in F1/F2 and are clamped by 1e-8 in F3;
+    NaN samples are zeroed by nan_to_num in F1/F2 and propagate in F3."""
+    import hipr_b200
+    img = smooth_image((48, 48), 9).astype(np.float64)
+    img[10:30, 10:30] = 0.25          # flat block
+    img[40, 5] = np.nan
+    got = hipr_b200.lne2d(_cuda(torch_cuda, img), flavour).cpu().numpy()
+    want = oracle.lne2d(img, flavour)
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    np.testing.assert_allclose(got, want, rtol=RTOL, atol=ATOL_F64, equal_nan=True)
+
+
+def test_lne2d_scale_invariance(torch_cuda):
+    """F1 is invariant to a power-of-two rescale of the image (exact in floating point)."""
+    import hipr_b200
+    img = smooth_image((64, 64), 10)
+    a = hipr_b200.lne2d(_cuda(torch_cuda, img), "F1").cpu().numpy()
+    b = hipr_b200.lne2d(_cuda(torch_cuda, img * 8.0), "F1").cpu().numpy()
+    assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("shape", [(40, 36, 95), (67, 129, 95), (33, 31, 63), (16, 16, 8), (9, 5, 130)])
+def test_channel_sum(torch_cuda, shape):
+    import hipr_b200
+    cube = (np.random.default_rng(11).random(shape) * 0.5).astype(np.float32)
+    want = cube.astype(np.float64).sum(axis=2)
+    for dt, tol in ((torch_cuda.float64, 1e-14), (torch_cuda.float32, 6e-8)):
+        got = hipr_b200.channel_sum(_cuda(torch_cuda, cube), normalize=False, dtype=dt).cpu().numpy()
+        np.testing.assert_allclose(got, want, rtol=tol, atol=0)
+        gotn = hipr_b200.channel_sum(_cuda(torch_cuda, cube), normalize=True, dtype=dt).cpu().numpy()
+        np.testing.assert_allclose(gotn, want / want.max(), rtol=2 * tol + 1e-15, atol=0)
+        assert gotn.max() == 1.0
+
+
+def test_channel_sum_calibration(torch_cuda):
+    import hipr_b200
+    rng = np.random.default_rng(12)
+    cube = rng.random((30, 41, 95)).astype(np.float32)
+    cal = (0.5 + rng.random((30, 41, 95))).astype(np.float32)
+    got = hipr_b200.channel_sum(_cuda(torch_cuda, cube), _cuda(torch_cuda, cal), normalize=False,
+                                dtype=torch_cuda.float64).cpu().numpy()
+    want = (cube.astype(np.float64) / cal.astype(np.float64)).sum(axis=2)
+    np.testing.assert_allclose(got, want, rtol=1e-14)
+
+
+ATOL_FIXED = 2e-7   # fixed-point stencil: float32 arithmetic on exact differences, float32 output
+ATOL_F32_SUM = 1e-5  # float32 SUM IMAGE: its 6e-8 rounding is amplified by value/line-range
+
+
+@pytest.mark.parametrize("flavour", ["F1", "F2", "F3"])
+@pytest.mark.parametrize("mode", ["fixed", "float32", "float64"])
+def test_neighbor2d_score_pipeline(torch_cuda, oracle, flavour, mode):
+    """The whole 2-D path on a synthetic FOV: cube -> sum -> /max -> pad -> stencil -> epilogue.
+    Default mode = float64 sums + fixed-point stencil: meets rtol 1e-5 with atol 2e-7."""
+    import hipr_b200
+    from hipr_b200 import synth
+    cube, _, _ = synth.make_fov(96, 160, 95, fov_index=3)
+    cube_np = cube.numpy()
+    dt = {"fixed": None, "float32": torch_cuda.float32, "float64": torch_cuda.float64}[mode]
+    got = hipr_b200.neighbor2d_score(cube.cuda(), flavour, dtype=dt).cpu().numpy()
+    want = oracle.neighbor2d_score(cube_np, flavour)
+    atol = {"fixed": ATOL_FIXED, "float32": ATOL_F32_SUM, "float64": ATOL_F64}[mode]
+    np.testing.assert_allclose(got, want, rtol=RTOL, atol=atol)
+
+
+@pytest.mark.parametrize("flavour", ["F1", "F2", "F3"])
+@pytest.mark.parametrize("shape", [(1, 1), (7, 3), (32, 32), (45, 77), (130, 97)])
+def test_lne2d_fixed_point(torch_cuda, oracle, flavour, shape):
+    """Fixed-point stencil on a float64 image against the float64 oracle of image / max."""
+    import hipr_b200
+    img = smooth_image(shape, 21).astype(np.float64) + 0.1
+    got = hipr_b200.lne2d_fixed(_cuda(torch_cuda, img), flavour).cpu().numpy()
+    want = oracle.lne2d(img / img.max(), flavour)
+    np.testing.assert_allclose(got, want, rtol=RTOL, atol=ATOL_FIXED, equal_nan=True)
+
+
+def test_lne2d_fixed_point_flat_regions_and_custom_table(torch_cuda, oracle):
+    import hipr_b200
+    img = smooth_image((64, 64), 22).astype(np.float64) + 0.1
+    img[20:45, 20:45] = 0.7
+    for flavour in ("F1", "F2", "F3"):
+        got = hipr_b200.lne2d_fixed(_cuda(torch_cuda, img), flavour).cpu().numpy()
+        want = oracle.lne2d(img / img.max(), flavour)
+        assert np.array_equal(np.isnan(got), np.isnan(want))
+        np.testing.assert_allclose(got, want, rtol=RTOL, atol=ATOL_FIXED, equal_nan=True)
+    flat = np.full((20, 20), 3.0)
+    got = hipr_b200.lne2d_fixed(_cuda(torch_cuda, flat), "F3").cpu().numpy()
+    np.testing.assert_allclose(got, oracle.lne2d(flat / 3.0, "F3"), atol=1e-12)
+    assert np.isnan(hipr_b200.lne2d_fixed(_cuda(torch_cuda, flat), "F1").cpu().numpy()).all()
+
+
+def test_neighbor2d_score_vs_compiled_reference(torch_cuda, oracle, ref2d):
+    import hipr_b200
+    from hipr_b200 import synth
+    cube, _, _ = synth.make_fov(64, 80, 95, fov_index=5)
+    want = oracle.neighbor2d_score(cube.numpy(), "F1", lp_func=ref2d.line_profile_2d_v2)
+    got = hipr_b200.neighbor2d_score(cube.cuda(), "F1", dtype=torch_cuda.float64).cpu().numpy()
+    np.testing.assert_allclose(got, want, rtol=RTOL, atol=ATOL_F64)
+    got = hipr_b200.neighbor2d_score(cube.cuda(), "F1").cpu().numpy()
+    np.testing.assert_allclose(got, want, rtol=RTOL, atol=ATOL_FIXED)
+
+
+def test_neighbor2d_score_batch_and_sum(torch_cuda, oracle):
+    import hipr_b200
+    from hipr_b200 import synth
+    cubes = torch_cuda.stack([synth.make_fov(48, 64, 95, fov_index=i)[0] for i in range(3)])
+    score, s = hipr_b200.neighbor2d_score(cubes.cuda(), "F1", return_sum=True)
+    assert score.shape == (3, 48, 64) and s.shape == (3, 48, 64)
+    for i in range(3):
+        want_s, _ = oracle.prologue(cubes[i].numpy())
+        np.testing.assert_allclose(s[i].cpu().numpy(), want_s / want_s.max(), rtol=2e-7)
+        np.testing.assert_allclose(score[i].cpu().numpy(), oracle.neighbor2d_score(cubes[i].numpy(), "F1"),
+                                   rtol=RTOL, atol=ATOL_FIXED)
+
+
+def test_host_entry_point(torch_cuda, oracle):
+    """hipr_neighbor2d_host: numpy in, numpy out, copies inside, banded H2D pipeline."""
+    import hipr_b200
+    from hipr_b200 import synth
+    cube = synth.make_fov(200, 333, 95, fov_index=8)[0].numpy()
+    score, s = hipr_b200.neighbor2d_score_host(cube, "F1", return_sum=True)
+    want_s, _ = oracle.prologue(cube)
+    np.testing.assert_allclose(s, want_s / want_s.max(), rtol=2e-7)
+    np.testing.assert_allclose(score, oracle.neighbor2d_score(cube, "F1"), rtol=RTOL, atol=ATOL_FIXED)
+    pinned = hipr_b200.pinned_empty(cube.shape, np.float32)
+    pinned[...] = cube
+    score2 = hipr_b200.neighbor2d_score_host(pinned, "F1")
+    assert np.array_equal(score, score2)
+
+
+def test_rejects_cpu_tensors_and_bad_arguments(torch_cuda):
+    import hipr_b200
+    with pytest.raises(ValueError):
+        hipr_b200.lne2d(torch_cuda.zeros(20, 20), "F1")              # CPU tensor: no CPU path
+    x = torch_cuda.zeros(20, 20, device="cuda")
+    with pytest.raises(ValueError):
+        hipr_b200.lne2d(x, "F9")
+    with pytest.raises(ValueError):
+        hipr_b200.lne2d(x, "F1", 10, 9)                              # even patch
+    with pytest.raises(TypeError):
+        hipr_b200.lne2d(x.to(torch_cuda.float16), "F1")
+    with pytest.raises(ValueError):
+        hipr_b200.lne2d(torch_cuda.zeros(8, 8, device="cuda"), "F1", padded=True)   # smaller than patch

@@ -1,0 +1,112 @@
+"""GPU parity, 3-D path (bio/neighbor.pyx) against the oracle."""
+import numpy as np
+import pytest
+
+from conftest import smooth_image
+
+pytestmark = pytest.mark.gpu
+RTOL, ATOL_F32, ATOL_F64 = 1e-5, 2e-6, 1e-12
+
+
+def _cuda(torch, a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.mark.parametrize("shape,params", [((3, 4, 5), (11, 9, 9)), ((9, 8, 33), (11, 9, 9)), ((6, 5, 7), (7, 5, 4)),
+                                           ((4, 4, 4), (5, 3, 3)), ((5, 6, 4), (9, 6, 7))])
+def test_line_profile_v2_bit_exact(torch_cuda, oracle, shape, params):
+    import neighbor
+    P = params[0]
+    a = np.random.default_rng(1).random(tuple(s + P - 1 for s in shape))
+    got = neighbor.line_profile_v2(a, *params)
+    want = oracle.line_profile_v2(a, *params)
+    assert got.shape == want.shape and got.dtype == np.float64
+    assert np.array_equal(got, want)
+
+
+def test_line_profile_v2_vs_compiled_reference(torch_cuda, ref3d):
+    import neighbor
+    a = np.random.default_rng(2).random((17, 19, 21))
+    assert np.array_equal(neighbor.line_profile_v2(a, 11, 9, 9), ref3d.line_profile_v2(a, 11, 9, 9))
+
+
+@pytest.mark.parametrize("shape,params", [((9, 10, 40), (11, 9, 9)), ((4, 3, 5), (11, 9, 9)), ((6, 5, 7), (7, 5, 4)),
+                                           ((5, 6, 4), (9, 6, 7))])
+def test_memory_efficient_v2(torch_cuda, oracle, shape, params):
+    import neighbor
+    P = params[0]
+    a = smooth_image(tuple(s + P - 1 for s in shape), 3).astype(np.float64)
+    got = neighbor.line_profile_memory_efficient_v2(a, *params)
+    want = oracle.line_profile_memory_efficient_v2(a, *params)
+    assert got.shape == want.shape
+    np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-15)
+
+
+def test_memory_efficient_v2_vs_compiled_reference(torch_cuda, ref3d):
+    import neighbor
+    a = smooth_image((14, 15, 16), 4).astype(np.float64)      # 4x5x6 voxels: the reference is slow
+    got = neighbor.line_profile_memory_efficient_v2(a, 11, 9, 9)
+    np.testing.assert_allclose(got, ref3d.line_profile_memory_efficient_v2(a, 11, 9, 9), rtol=1e-12, atol=1e-15)
+
+
+def test_memory_efficient_v2_flat_lines_clamped(torch_cuda, oracle):
+    import neighbor
+    a = np.full((15, 15, 15), 0.5)
+    a[7, 7, 7] = 0.5 + 1e-9
+    got = neighbor.line_profile_memory_efficient_v2(a, 11, 9, 9)
+    want = oracle.line_profile_memory_efficient_v2(a, 11, 9, 9)
+    assert not np.isnan(got).any()
+    np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-15)
+
+
+@pytest.mark.parametrize("flavour", ["F2", "F3", "ME2"])
+@pytest.mark.parametrize("dtype_name", ["float32", "float64"])
+def test_lne3d(torch_cuda, oracle, flavour, dtype_name):
+    import hipr_b200
+    vol = smooth_image((12, 17, 40), 5)
+    v = vol.astype(np.float64) if dtype_name == "float64" else vol
+    got = hipr_b200.lne3d(_cuda(torch_cuda, v), flavour).cpu().numpy()
+    want = oracle.lne3d(vol.astype(np.float64), flavour)
+    np.testing.assert_allclose(got, want, rtol=RTOL, atol=ATOL_F64 if dtype_name == "float64" else ATOL_F32)
+
+
+@pytest.mark.parametrize("flavour", ["F2", "F3", "ME2"])
+def test_lne3d_generic_parameters(torch_cuda, oracle, flavour):
+    import hipr_b200
+    vol = smooth_image((9, 8, 11), 6).astype(np.float64)
+    got = hipr_b200.lne3d(_cuda(torch_cuda, vol), flavour, 7, 5, 4).cpu().numpy()
+    want = oracle.lne3d(vol, flavour, 7, 5, 4)
+    np.testing.assert_allclose(got, want, rtol=RTOL, atol=ATOL_F64)
+
+
+def test_memory_efficient_v3(torch_cuda, oracle, ref3d):
+    """v3 reads outside its patch (flat addressing): equal to the oracle everywhere, NaN exactly
+    where the reference's read leaves the buffer, and equal to the compiled reference elsewhere."""
+    import neighbor
+    a = smooth_image((24, 15, 14), 7).astype(np.float64)
+    got = neighbor.line_profile_memory_efficient_v3(a, 11, 9, 9)
+    want = oracle.line_profile_memory_efficient_v3(a, 11, 9, 9)
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-12, equal_nan=True)
+    ok = ~np.isnan(got)
+    assert ok.any()
+    ref = ref3d.line_profile_memory_efficient_v3(a, 11, 9, 9)
+    np.testing.assert_allclose(got[ok], ref[ok], rtol=1e-9, atol=1e-12)
+
+
+def test_neighbor3d_score_pipeline(torch_cuda, oracle):
+    import hipr_b200
+    from hipr_b200 import synth
+    cube = synth.make_volume_cube(10, 12, 36, 95, seed=5)
+    got = hipr_b200.neighbor3d_score(cube.cuda(), "ME2", dtype=torch_cuda.float64).cpu().numpy()
+    s, _ = oracle.prologue(cube.numpy())
+    want = oracle.lne3d(s / s.max(), "ME2")
+    np.testing.assert_allclose(got, want, rtol=RTOL, atol=ATOL_F64)
+
+
+def test_dead_functions_fail_like_the_reference(torch_cuda):
+    import neighbor
+    with pytest.raises(ValueError, match="Buffer dtype mismatch"):
+        neighbor.neighbor_average(np.zeros((30, 30, 30), np.float32), 11)
+    with pytest.raises(ValueError, match="Buffer dtype mismatch"):
+        neighbor.line_profile(np.zeros((12, 12, 12)), 11, 9, 9)
