@@ -1,0 +1,390 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the HiPR-FISH spectral-segmentation front end on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path
+
+Metric (BASELINE.json): neighbor2d Mpix/s at 2048^2 x 95 channels.  A step is one pass of the
+hot path (channel sum -> /max -> edge pad -> 9x11 line profiles -> F1 epilogue, i.e.
+syn/..._measurement.py:105-124 without the skimage denoise) over one synthetic 2048x2048x95
+float32 field of view per GPU (BASELINE config 2; with N GPUs each rank has its own FOVs -- config
+3's FOV sharding, no collective, weak scaling).  The per-cell mean-spectrum reduction
+(syn/..._measurement.py:167-172) is timed in a second region and reported as cells/s.
+
+value      : device-resident throughput, CUDA events around exactly K steps, max over ranks.
+e2e        : the same pipeline through the C ABI's host-buffer entry point
+             (hipr_neighbor2d_host): pinned host cube -> H2D -> kernels -> D2H score, every step.
+roofline   : the dominant kernel (channel sum, K1), 384 B/pixel algorithmic,
+             its launches timed with CUDA events inside the timed region.
+cpu_baseline: the compiled reference Cython (oracle/_ref) + the scripts' numpy blocks, one core,
+             on a bounded crop of the same FOV.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "hiprfish-image-analysis_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+H = W = 2048
+C = 95
+BYTES_PER_PIXEL = 4 * C + 4          # read the cube once, write the score map
+METRIC = "neighbor2d Mpix/s at 2048x2048x95ch"
+WORKLOAD = "c2: one synthetic 2048x2048x95 float32 FOV per GPU per step (FOV-sharded, BASELINE config 2/3)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--pool", type=int, default=2, help="resident FOVs per GPU that the steps rotate over")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="host-buffer steps (0: min(steps, 10))")
+    ap.add_argument("--cpu-sample", type=int, default=1024, help="side of the CPU-baseline crop")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--streams", type=int, default=1, help="CUDA streams the independent FOVs alternate over")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU legs (the only place bench.py touches oracle/)
+# ------------------------------------------------------------------------------------------------
+
+def _lp2d():
+    from oracle import load_ref, hipr_oracle
+    ref = load_ref("neighbor2d")
+    if ref is not None:
+        return ref.line_profile_2d_v2, "reference"
+    return hipr_oracle.line_profile_2d_v2, "port"
+
+
+def cpu_single_core(cube_np):
+    """The reference path on one core (it is single-threaded): returns seconds."""
+    from oracle import hipr_oracle
+    lp, kind = _lp2d()
+    t0 = time.perf_counter()
+    hipr_oracle.neighbor2d_score(cube_np, "F1", lp_func=lp)
+    return time.perf_counter() - t0, kind
+
+
+_G = {}
+
+
+def _band_sum(args):
+    r0, r1 = args
+    import numpy as np
+    return np.sum(_G["cube"][r0:r1], axis=2)
+
+
+def _band_score(args):
+    from oracle import hipr_oracle
+    padded_band, = args
+    lp, _ = _lp2d()
+    return hipr_oracle.epilogue_F1(lp(padded_band, 11, 9))
+
+
+def reference_step(pool, cube_np, nproc):
+    """One pass of the reference path over `cube_np` with `nproc` worker processes over row bands
+    (the reference's own parallelism is `snakemake -j` over independent images; bands of one image
+    with a 5-row halo compute exactly the same thing)."""
+    import numpy as np
+    Hs = cube_np.shape[0]
+    edges = np.linspace(0, Hs, nproc + 1).astype(int)
+    bands = [(int(a), int(b)) for a, b in zip(edges[:-1], edges[1:]) if b > a]
+    sums = pool.map(_band_sum, bands)
+    s = np.concatenate(sums, axis=0)
+    s = s / np.max(s)
+    padded = np.pad(s, 5, mode="edge").astype(np.float64)
+    parts = pool.map(_band_score, [(padded[a:b + 10],) for a, b in bands])
+    return np.concatenate(parts, axis=0)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    import numpy as np
+    import torch
+    from hipr_b200 import synth
+    for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
+        os.environ[k] = "1"          # as syn/Snakefile:13-14
+    cores = len(os.sched_getaffinity(0))
+    side = args.cpu_sample
+    # bounded sample: a side x side crop of FOV 0 per step, sized so K steps take minutes at most
+    cube = synth.make_fov(side, side, C, fov_index=0)[0].numpy()
+    _G["cube"] = cube
+    _, kind = _lp2d()
+    ctx = mp.get_context("fork")
+    nproc = max(1, min(cores, side // 32))
+    with ctx.Pool(nproc) as pool:
+        for _ in range(max(args.warmup, 1)):
+            reference_step(pool, cube, nproc)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            reference_step(pool, cube, nproc)
+        dt = time.perf_counter() - t0
+    mpix_s = side * side * args.steps / dt / 1e6
+    line = {
+        "impl": "reference", "metric": METRIC, "value": mpix_s, "unit": "Mpix/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "flavour": "F1", "patch_size": 11, "phi_range": 9},
+        "cpu_baseline": {"value": mpix_s, "unit": "Mpix/s", "cores": nproc, "kind": kind,
+                         "sample": "%dx%dx%d crop of FOV 0 per step, %d worker processes over row bands"
+                                   % (side, side, C, nproc)},
+        "e2e": {"value": mpix_s, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def sample(self):
+        if self.nv is None:
+            return
+        try:
+            self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+            mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            for bit, name in self.REASONS.items():
+                if mask & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            self.sample()
+            time.sleep(0.001)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------------
+# the CUDA arm
+# ------------------------------------------------------------------------------------------------
+
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import hipr_b200
+    from hipr_b200 import ops, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    lib = hipr_b200.lib()
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback")
+
+    # resident inputs: `pool` FOVs per GPU, FOV index = rank + world * i (config 3's sharding)
+    pool = [synth.make_fov(H, W, C, fov_index=rank + world * i, device=dev) for i in range(args.pool)]
+    cubes = [p[0] for p in pool]
+    labels = [p[1] for p in pool]
+    max_labels = [int(ops.label_max(l).item()) for l in labels]
+    npix = H * W
+
+    streams = [torch.cuda.Stream(device=dev) for _ in range(args.streams)] if args.streams > 1 else None
+
+    def step(i, ev=None):
+        cube = cubes[i % len(cubes)]
+        st = streams[i % len(streams)] if streams else torch.cuda.current_stream()
+        with torch.cuda.stream(st):
+            if ev:
+                ev[0].record(st)
+            s, mk = ops.channel_sum(cube, None, normalize=False, dtype=torch.float64, return_max=True)
+            if ev:
+                ev[1].record(st)
+            out = ops.lne2d_fixed(s, "F1", 11, 9, padded=False, range_keys=mk)
+        return out
+
+    def fork():
+        if streams:
+            for st in streams:
+                st.wait_stream(torch.cuda.current_stream())
+
+    def join():
+        if streams:
+            for st in streams:
+                torch.cuda.current_stream().wait_stream(st)
+
+    # ---- headline timed region ------------------------------------------------------------------
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    # hold the clocks up: ~0.25 s more of the same work before the timed region (untimed)
+    t_end = time.perf_counter() + 0.25
+    while time.perf_counter() < t_end:
+        step(0)
+        torch.cuda.synchronize()
+    k1_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local)
+    barrier()
+    launches0 = lib.hipr_launch_count()
+    sampler.start()
+    e0.record()
+    fork()
+    for i in range(args.steps):
+        step(i, k1_events[i])
+    join()
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    launches = lib.hipr_launch_count() - launches0
+    ms = e0.elapsed_time(e1)
+    k1_ms = sum(a.elapsed_time(b) for a, b in k1_events) / args.steps
+
+    # ---- per-cell spectra region ----------------------------------------------------------------
+    def cell_step(i):
+        j = i % len(cubes)
+        sums, counts = ops.cell_spectra_accumulate(cubes[j], labels[j], max_labels[j])
+        return sums, counts
+
+    for i in range(3):
+        cell_step(i)
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    c0.record()
+    for i in range(args.steps):
+        cell_step(i)
+    c1.record()
+    barrier()
+    cell_ms = c0.elapsed_time(c1)
+    n_cells = [int(ops.cell_spectra_finalize(*cell_step(j))[0].numel()) for j in range(len(cubes))]
+    cells_per_step = sum(n_cells) / len(n_cells)
+    fg_frac = float(sum((l > 0).float().mean().item() for l in labels) / len(labels))
+
+    # ---- end to end through the host-buffer C ABI -----------------------------------------------
+    e2e_steps = args.e2e_steps or min(args.steps, 10)
+    host = ops.pinned_empty((H, W, C), np.float32)
+    torch.from_numpy(host).copy_(cubes[0].cpu())
+    score_host = ops.pinned_empty((H, W), np.float32)
+    for _ in range(2):
+        ops.neighbor2d_score_host(host, "F1", out=score_host)
+    barrier()
+    e2e_dev_ms = 0.0
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ops.neighbor2d_score_host(host, "F1", out=score_host)
+        e2e_dev_ms += lib.hipr_host_last_elapsed_ms()
+    torch.cuda.synchronize()
+    e2e_wall_ms = 1e3 * (time.perf_counter() - t0)
+    score_check = float(score_host.mean())
+
+    # ---- reduce over ranks (max time) -----------------------------------------------------------
+    t = torch.tensor([ms, cell_ms, e2e_dev_ms, e2e_wall_ms, k1_ms], dtype=torch.float64, device=dev)
+    cnt = torch.tensor([launches, cells_per_step], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    ms, cell_ms, e2e_dev_ms, e2e_wall_ms, k1_ms = [float(x) for x in t.tolist()]
+    launches, cells_all = int(cnt[0].item()), float(cnt[1].item())
+
+    if rank == 0:
+        value = world * npix * args.steps / (ms * 1e-3) / 1e6
+        k1_gbs = npix * BYTES_PER_PIXEL / (k1_ms * 1e-3) / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))["chansum_bytes_per_launch"]
+        except Exception:
+            pass
+        line = {
+            "metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "flavour": "F1", "patch_size": 11, "phi_range": 9,
+                       "l2": "inputs larger than L2 (1.59 GB cube per step, %d FOVs in rotation)" % len(cubes),
+                       "arithmetic": "float64 channel sums, 31-bit fixed-point stencil, float32 score"},
+            "pipeline_frac_of_hbm_peak": value / world * 1e6 * BYTES_PER_PIXEL / 1e9 / hbm_peak,
+            "roofline": {"bound": "hbm", "kernel": "chansum_bulk_kernel", "achieved": k1_gbs, "peak": hbm_peak,
+                         "unit": "GB/s", "frac": k1_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": npix * BYTES_PER_PIXEL, "ms_per_launch": k1_ms},
+            "e2e": {"value": world * npix * e2e_steps / (e2e_dev_ms * 1e-3) / 1e6, "unit": "Mpix/s",
+                    "h2d_bytes_per_step": npix * C * 4, "d2h_bytes_per_step": npix * 4, "steps": e2e_steps,
+                    "ms_per_step": e2e_dev_ms / e2e_steps, "wall_ms_per_step": e2e_wall_ms / e2e_steps,
+                    "api": "hipr_neighbor2d_host (C ABI, pinned host buffers)", "score_mean": score_check},
+            "cell_spectra": {"cells_per_s": cells_all * args.steps / (cell_ms * 1e-3),
+                             "mpix_per_s": world * npix * args.steps / (cell_ms * 1e-3) / 1e6,
+                             "ms_per_step": cell_ms / args.steps, "cells_per_fov": cells_all / world,
+                             "foreground_fraction": fg_frac,
+                             "algorithmic_gbs": npix * BYTES_PER_PIXEL / (cell_ms / args.steps * 1e-3) / 1e9,
+                             "frac_of_hbm_peak": npix * BYTES_PER_PIXEL / (cell_ms / args.steps * 1e-3) / 1e9 / hbm_peak,
+                             "note": "background pixels' channel vectors are never fetched, so the algorithmic "
+                                     "384 B/px rate can exceed the HBM peak"},
+            "gpu_launches": launches, "clocks": clocks,
+        }
+        if not args.no_cpu and world == 1:
+            side = args.cpu_sample
+            crop = cubes[0][:side, :side].cpu().numpy()
+            for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
+                os.environ[k] = "1"
+            sec, kind = cpu_single_core(crop)
+            line["cpu_baseline"] = {"value": side * side / sec / 1e6, "unit": "Mpix/s", "cores": 1, "kind": kind,
+                                    "sample": "%dx%dx%d crop of the step's FOV, single process (the reference is "
+                                              "single-threaded), %.1f s" % (side, side, C, sec),
+                                    "host_cores_available": len(os.sched_getaffinity(0))}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

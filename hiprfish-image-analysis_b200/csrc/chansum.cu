@@ -181,6 +181,14 @@ image_range_kernel(const T *__restrict__ a, int64_t n, unsigned long long *__res
 __global__ void maxkey_decode_kernel(const unsigned long long *__restrict__ k, double *__restrict__ out) {
     *out = double_of_key(*k);
 }
+__global__ void range_decode_kernel(const unsigned long long *__restrict__ k, double *__restrict__ out) {
+    out[0] = double_of_key(k[0]);
+    out[1] = double_of_key(k[1]);
+}
+__global__ void range_encode_kernel(const double *__restrict__ v, unsigned long long *__restrict__ k) {
+    k[0] = key_of_double(v[0]);
+    k[1] = key_of_double(v[1]);
+}
 
 template <typename OutT>
 static int chansum_launch(const float *cube, const float *calib, int64_t npix, int C, OutT *out,
@@ -298,5 +306,19 @@ extern "C" int hipr_image_range(const void *image_dev, int dtype, int64_t n, uin
         image_range_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((const float *)image_dev, n, rg);
     else
         image_range_kernel<double><<<(unsigned)blocks, 256, 0, st>>>((const double *)image_dev, n, rg);
+    return after_launch();
+}
+
+extern "C" int hipr_range_decode(const uint64_t *range_dev, double *maxmin_dev, void *stream) {
+    if (!range_dev || !maxmin_dev) return HIPR_E_ARG;
+    range_decode_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(reinterpret_cast<const unsigned long long *>(range_dev),
+                                                          maxmin_dev);
+    return after_launch();
+}
+
+extern "C" int hipr_range_encode(const double *maxmin_dev, uint64_t *range_dev, void *stream) {
+    if (!range_dev || !maxmin_dev) return HIPR_E_ARG;
+    range_encode_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(maxmin_dev,
+                                                          reinterpret_cast<unsigned long long *>(range_dev));
     return after_launch();
 }

@@ -17,6 +17,8 @@ struct Workspace {
     std::mutex mu;
     cudaStream_t copy = nullptr, comp = nullptr;
     cudaEvent_t copied[NBUF] = {}, freed[NBUF] = {}, done = nullptr;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;   // device-side timing of the last host call
+    float last_ms = -1.f;
     void *band[NBUF] = {};
     size_t band_bytes = 0;
     void *aux[6] = {};
@@ -34,6 +36,8 @@ static int ws_init(Workspace &w) {
         HIPR_CUDA(cudaEventCreateWithFlags(&w.freed[i], cudaEventDisableTiming));
     }
     HIPR_CUDA(cudaEventCreateWithFlags(&w.done, cudaEventDisableTiming));
+    HIPR_CUDA(cudaEventCreate(&w.t0));
+    HIPR_CUDA(cudaEventCreate(&w.t1));
     w.ready = true;
     return HIPR_OK;
 }
@@ -142,6 +146,8 @@ extern "C" int hipr_neighbor2d_host(const float *cube_host, int H, int W, int C,
     double *sum_dev = (double *)w.aux[0];
     float *score_dev = (float *)w.aux[1];
     unsigned long long *key = (unsigned long long *)w.aux[2];
+    HIPR_CUDA(cudaEventRecord(w.t0, w.copy));            // device clock starts before the first H2D
+    HIPR_CUDA(cudaStreamWaitEvent(w.comp, w.t0, 0));
     HIPR_CUDA(cudaMemsetAsync(key, 0x00, 8, w.comp));
     HIPR_CUDA(cudaMemsetAsync(key + 1, 0xff, 8, w.comp));
     int b = 0;
@@ -174,9 +180,13 @@ extern "C" int hipr_neighbor2d_host(const float *cube_host, int H, int W, int C,
         if ((e = hipr_normalize_cast(sum_dev, (int64_t)H * W, (const uint64_t *)key, score_dev, w.comp))) return e;
         HIPR_CUDA(cudaMemcpyAsync(sum_host, score_dev, img_bytes, cudaMemcpyDeviceToHost, w.comp));
     }
+    HIPR_CUDA(cudaEventRecord(w.t1, w.comp));            // ... and stops after the last D2H
     HIPR_CUDA(cudaStreamSynchronize(w.comp));
+    HIPR_CUDA(cudaEventElapsedTime(&w.last_ms, w.t0, w.t1));
     return HIPR_OK;
 }
+
+extern "C" double hipr_host_last_elapsed_ms(void) { return (double)g_ws.last_ms; }
 
 extern "C" int hipr_cell_spectra_host(const float *cube_host, const void *labels_host, int label_bytes, int64_t npix,
                                       int C, int64_t capacity, int64_t *n_cells, int64_t *labels_out,

@@ -20,6 +20,8 @@ _SIGNATURES = {
     "hipr_normalize_cast": (_i, [_vp, _i64, _vp, _vp, _vp]),
     "hipr_normalize": (_i, [_vp, _i, _i64, _vp, _vp]),
     "hipr_maxkey_decode": (_i, [_vp, _vp, _vp]),
+    "hipr_range_decode": (_i, [_vp, _vp, _vp]),
+    "hipr_range_encode": (_i, [_vp, _vp, _vp]),
     "hipr_line_profile_2d": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "hipr_lne2d": (_i, [_vp, _i, _i, _i64, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp]),
     "hipr_lne2d_q": (_i, [_vp, _i, _i, _i64, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp]),
@@ -31,6 +33,7 @@ _SIGNATURES = {
     "hipr_cell_spectra_finalize": (_i, [_vp, _vp, _i64, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "hipr_neighbor2d_host": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp]),
     "hipr_cell_spectra_host": (_i, [_vp, _vp, _i, _i64, _i, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "hipr_host_last_elapsed_ms": (C.c_double, []),
     "hipr_host_alloc": (_i, [C.POINTER(_vp), _i64]),
     "hipr_host_free": (_i, [_vp]),
     "hipr_host_release_workspace": (_i, []),

@@ -52,15 +52,32 @@ class MaxKey:
     """Two device scalars: max and min of an image as order-preserving keys (see hipr_b200.h)."""
 
     def __init__(self, device):
-        self.key = torch.zeros(2, dtype=torch.int64, device=device)
+        # filled (and reset) by hipr_chansum / hipr_image_range; no torch kernel on the hot path
+        self.key = torch.empty(2, dtype=torch.int64, device=device)
 
     def ptr(self):
         return C.c_void_p(self.key.data_ptr())
 
     def value(self):
         out = torch.empty(1, dtype=torch.float64, device=self.key.device)
-        check(lib().hipr_maxkey_decode(self.ptr(), C.c_void_p(out.data_ptr()), _stream()), "maxkey_decode")
+        with torch.cuda.device(self.key.device):
+            check(lib().hipr_maxkey_decode(self.ptr(), C.c_void_p(out.data_ptr()), _stream()), "maxkey_decode")
         return out
+
+    def values(self):
+        """(max, min) as 1-element float64 device tensors."""
+        out = torch.empty(2, dtype=torch.float64, device=self.key.device)
+        with torch.cuda.device(self.key.device):
+            check(lib().hipr_range_decode(self.ptr(), C.c_void_p(out.data_ptr()), _stream()), "range_decode")
+        return out[0:1], out[1:2]
+
+    @classmethod
+    def from_values(cls, vmax, vmin):
+        mm = torch.cat([vmax.reshape(1), vmin.reshape(1)]).to(torch.float64).contiguous()
+        mk = cls(mm.device)
+        with torch.cuda.device(mm.device):
+            check(lib().hipr_range_encode(C.c_void_p(mm.data_ptr()), mk.ptr(), _stream()), "range_encode")
+        return mk
 
 
 def channel_sum(cube, calibration=None, normalize=True, dtype=torch.float32, return_max=False):

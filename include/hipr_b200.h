@@ -89,6 +89,11 @@ int hipr_normalize(void *sum_dev, int sum_dtype, int64_t npix, const uint64_t *m
 /* decode the key into a double on the device (for callers that want the scalar) */
 int hipr_maxkey_decode(const uint64_t *maxkey_dev, double *max_dev, void *stream);
 
+/* range keys <-> doubles on the device: maxmin_dev[0] = max, [1] = min (used around the
+ * cross-GPU all-reduce of a split mosaic's range) */
+int hipr_range_decode(const uint64_t *range_dev, double *maxmin_dev, void *stream);
+int hipr_range_encode(const double *maxmin_dev, uint64_t *range_dev, void *stream);
+
 /* ---- 2-D literal stencil ------------------------------------------------------------------
  * Replaces line_profile_2d_v2(image_padded, patch_size, phi_range), eco/neighbor2d.pyx:8-64:
  *   out[i, j, t, li] = image_padded[i + table[t, li, 0], j + table[t, li, 1]]
@@ -186,6 +191,9 @@ int hipr_cell_spectra_host(const float *cube_host, const void *labels_host, int 
                            int64_t npix, int C, int64_t capacity, int64_t *n_cells,
                            int64_t *labels_out, int64_t *area_out, double *avgint_out,
                            double *avgint_norm_out);
+/* device-clock duration (CUDA events: before the first H2D .. after the last D2H) of the most
+ * recent hipr_neighbor2d_host call in this process, in ms; negative if none yet */
+double hipr_host_last_elapsed_ms(void);
 int hipr_host_alloc(void **ptr, int64_t bytes);   /* page-locked host memory */
 int hipr_host_free(void *ptr);
 int hipr_host_release_workspace(void);            /* frees cached device buffers/streams */

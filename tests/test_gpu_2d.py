@@ -238,3 +238,26 @@ def test_rejects_cpu_tensors_and_bad_arguments(torch_cuda):
         hipr_b200.lne2d(x.to(torch_cuda.float16), "F1")
     with pytest.raises(ValueError):
         hipr_b200.lne2d(torch_cuda.zeros(8, 8, device="cuda"), "F1", padded=True)   # smaller than patch
+
+
+def test_mosaic_slabs_equal_unsplit_single_gpu(torch_cuda, oracle):
+    """Config 5 on one GPU: row slabs + 5-row halos + the GLOBAL range give exactly the unsplit
+    score (what sharding.MosaicSlab computes after its halo exchange and range all-reduce)."""
+    import hipr_b200
+    from hipr_b200 import ops, sharding, synth
+    cube = synth.make_fov(96, 128, 95, fov_index=11)[0].cuda()
+    s, mk = ops.channel_sum(cube, None, normalize=False, dtype=torch_cuda.float64, return_max=True)
+    whole = ops.lne2d_fixed(s, "F1", range_keys=mk)
+    vmax, vmin = mk.values()
+    world = 3
+    for rank in range(world):
+        r0, r1 = sharding.slab_bounds(96, rank, world)
+        s_slab, mk_slab = ops.channel_sum(cube[r0:r1], None, normalize=False, dtype=torch_cuda.float64, return_max=True)
+        assert torch_cuda.equal(s_slab, s[r0:r1])
+        lmax, lmin = mk_slab.values()
+        assert float(lmax) <= float(vmax) and float(lmin) >= float(vmin)
+        nt, nb = (0 if rank == 0 else 5), (0 if rank == world - 1 else 5)
+        ext = s[r0 - nt: r1 + nb].contiguous()
+        got = ops.lne2d_fixed(ext, "F1", range_keys=ops.MaxKey.from_values(vmax, vmin))[nt: ext.shape[0] - nb]
+        assert torch_cuda.equal(got, whole[r0:r1])
+    np.testing.assert_allclose(whole.cpu().numpy(), oracle.neighbor2d_score(cube.cpu().numpy(), "F1"), rtol=RTOL, atol=ATOL_FIXED)

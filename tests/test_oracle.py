@@ -1,0 +1,121 @@
+"""The oracle is pinned: against the compiled, unmodified reference (oracle/_ref) where it is built,
+and against golden vectors generated from it (tests/golden/make_golden.py) everywhere."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from conftest import smooth_image
+
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_vectors.npz"))
+SHA_2D = "b1278799e8f5fd61d163437987943d3b2d104245e493df6dab5f2072335dbb3d"
+SHA_3D = "13bca0604962da5b1568581024e69ea5f4079c9ad9b04745a4beec04a8d93040"
+
+
+def test_tables_match_survey_hashes_and_golden(oracle):
+    t2 = oracle.line_table_2d(11, 9).transpose(2, 0, 1)
+    t3 = oracle.line_table_3d(11, 9, 9).transpose(2, 0, 1)
+    assert hashlib.sha256((t2 - 5).astype(np.int64).tobytes()).hexdigest() == SHA_2D
+    assert hashlib.sha256((t3 - 5).astype(np.int64).tobytes()).hexdigest() == SHA_3D
+    assert np.array_equal(t2, GOLD["table2d_11_9"])
+    assert np.array_equal(t3, GOLD["table3d_11_9_9"])
+    # phi3 and phi6 are not mirror images (np.round of 2.5000000000000004 vs -2.4999999999999996)
+    assert (t2[3, 0] - 5).tolist() == [-3, -4] and (t2[6, 0] - 5).tolist() == [2, -4]
+    assert all((t2[:, 5] == 5).ravel()) and all((t3[:, 5] == 5).ravel())     # centre sample is the pixel itself
+    assert len({tuple(p) for p in (t2 - 5).reshape(-1, 2)}) == 64             # 64 distinct footprint pixels
+    assert len({tuple(p) for p in (t3 - 5).reshape(-1, 3)}) == 355
+    assert len({tuple(map(tuple, d)) for d in t3}) == 66                      # 66 of 72 lines distinct
+
+
+def test_golden_2d(oracle):
+    img = GOLD["img2d"]
+    padded = np.pad(img / img.max(), 5, mode="edge")
+    lp = oracle.line_profile_2d_v2(padded, 11, 9)
+    assert hashlib.sha256(lp.tobytes()).digest() == GOLD["lp2d_sha256"].tobytes()
+    assert np.array_equal(lp[:3, :4], GOLD["lp2d_corner"])
+    for f in ("F1", "F2", "F3"):
+        assert np.array_equal(oracle.EPILOGUES[f](lp), GOLD["score2d_" + f], equal_nan=True)
+        assert np.array_equal(oracle.lne2d(img / img.max(), f), GOLD["score2d_" + f], equal_nan=True)
+
+
+def test_golden_3d(oracle):
+    vol = GOLD["vol3d"]
+    vp = np.pad(vol / vol.max(), 5, mode="edge")
+    lp5 = oracle.line_profile_v2(vp, 11, 9, 9)
+    assert hashlib.sha256(lp5.tobytes()).digest() == GOLD["lp3d_sha256"].tobytes()
+    assert np.array_equal(oracle.line_profile_memory_efficient_v2(vp, 11, 9, 9), GOLD["me2_3d"])
+    assert np.array_equal(oracle.lne3d(vol / vol.max(), "ME2"), GOLD["score3d_ME2"])
+    assert np.array_equal(oracle.lne3d(vol / vol.max(), "F2"), GOLD["score3d_F2"])
+    assert np.array_equal(oracle.lne3d(vol / vol.max(), "F3"), GOLD["score3d_F3"])
+    got = oracle.line_profile_memory_efficient_v3(GOLD["v3_in"], 11, 9, 9)[:6]
+    assert not np.isnan(got).any()
+    assert np.array_equal(got, GOLD["v3_out"])
+
+
+def test_golden_pipeline_and_cells(oracle):
+    cube, lab = GOLD["cube"], GOLD["labels"]
+    assert np.array_equal(oracle.neighbor2d_score(cube, "F1"), GOLD["cube_score_F1"])
+    l, a, avg, norm = oracle.cell_spectra(lab, cube)
+    assert np.array_equal(l, GOLD["cell_labels"]) and np.array_equal(a, GOLD["cell_area"])
+    assert np.array_equal(avg, GOLD["cell_avgint"]) and np.array_equal(norm, GOLD["cell_avgint_norm"])
+    assert l.tolist() == [3, 7, 12]
+
+
+@pytest.mark.parametrize("params", [(11, 9), (7, 5), (11, 4), (15, 9), (11, 12), (5, 3), (13, 16)])
+def test_line_profile_2d_vs_compiled_reference(oracle, ref2d, params):
+    P, R = params
+    a = np.random.default_rng(P * 100 + R).random((P + 12, P + 16))
+    assert np.array_equal(ref2d.line_profile_2d_v2(a, P, R), oracle.line_profile_2d_v2(a, P, R))
+
+
+@pytest.mark.parametrize("params", [(11, 9, 9), (7, 5, 4), (9, 6, 7), (5, 3, 3)])
+def test_3d_vs_compiled_reference(oracle, ref3d, params):
+    P = params[0]
+    a = np.random.default_rng(sum(params)).random((P + 10, P + 4, P + 3))
+    assert np.array_equal(ref3d.line_profile_v2(a, *params), oracle.line_profile_v2(a, *params))
+    small = a[:P + 2, :P + 2, :P + 1]                       # the reference's me_v2 runs at ~3 kvox/s
+    assert np.array_equal(ref3d.line_profile_memory_efficient_v2(small, *params),
+                          oracle.line_profile_memory_efficient_v2(small, *params))
+    got = oracle.line_profile_memory_efficient_v3(a, *params)
+    ok = ~np.isnan(got)
+    assert ok.any()
+    assert np.array_equal(ref3d.line_profile_memory_efficient_v3(a, *params)[ok], got[ok])
+
+
+def test_identities_from_the_survey(oracle):
+    """me_v2 == (v2[..., 5] - min) / max(max - min, 1e-8); percentiles of 9 values are order
+    statistics 2 and 6; of 72 values they are lerps at 17.75 / 53.25."""
+    a = smooth_image((15, 14, 16), 1).astype(np.float64)
+    lp = oracle.line_profile_v2(a, 11, 9, 9)
+    mn, mx = lp.min(-1), lp.max(-1)
+    assert np.array_equal(oracle.line_profile_memory_efficient_v2(a, 11, 9, 9), (lp[..., 5] - mn) / np.maximum(mx - mn, 1e-8))
+    v = np.random.default_rng(0).random((50, 9))
+    s = np.sort(v, axis=1)
+    assert np.array_equal(np.percentile(v, 25, axis=1), s[:, 2]) and np.array_equal(np.percentile(v, 75, axis=1), s[:, 6])
+    v = np.random.default_rng(1).random((50, 72))
+    s = np.sort(v, axis=1)
+    assert np.array_equal(np.percentile(v, 25, axis=1), s[:, 18] - (s[:, 18] - s[:, 17]) * 0.25)
+    assert np.array_equal(np.percentile(v, 75, axis=1), s[:, 53] + (s[:, 54] - s[:, 53]) * 0.25)
+
+
+def test_cell_spectra_matches_scipy_ndimage(oracle):
+    """regionprops(...).mean_intensity is the per-label arithmetic mean: cross-check with scipy."""
+    from scipy import ndimage
+    rng = np.random.default_rng(5)
+    lab = (rng.integers(0, 40, (60, 70)) * (rng.random((60, 70)) > 0.4)).astype(np.int64)
+    lab[lab == 17] = 0                                   # a missing id: rows are the labels present
+    img = rng.random((60, 70, 12))
+    labels, area, avg, norm = oracle.cell_spectra(lab, img)
+    assert labels.tolist() == sorted(set(np.unique(lab)) - {0}) and 17 not in labels
+    assert np.array_equal(area, ndimage.sum_labels(np.ones_like(lab), lab, labels).astype(np.int64))
+    for k in range(12):
+        np.testing.assert_allclose(avg[:, k], ndimage.mean(img[:, :, k], lab, labels), rtol=1e-13)
+    np.testing.assert_allclose(norm, avg / avg.max(axis=1)[:, None])
+
+
+def test_reference_errors(ref2d, ref3d):
+    with pytest.raises(ValueError, match="Buffer dtype mismatch"):
+        ref2d.line_profile_2d_v2(np.zeros((12, 12), np.float32), 11, 9)
+    with pytest.raises(ValueError, match="Buffer dtype mismatch"):
+        ref3d.neighbor_average(np.zeros((30, 30, 30), np.float32), 11)
