@@ -49,7 +49,15 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=0, help="host-buffer steps (0: min(steps, 10))")
     ap.add_argument("--cpu-sample", type=int, default=1024, help="side of the CPU-baseline crop")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
-    ap.add_argument("--streams", type=int, default=1, help="CUDA streams the independent FOVs alternate over")
+    ap.add_argument("--streams", type=int, default=2,
+                    help="CUDA streams consecutive (independent) FOVs alternate over; 2 lets FOV i+1's channel sum "
+                         "run under FOV i's stencil")
+    ap.add_argument("--path", default="pipeline", choices=["pipeline", "fused", "two-kernel"],
+                    help="pipeline: hipr_neighbor2d, one C-ABI call per FOV = channel sum + fixed-point stencil "
+                         "(default); fused: one launch per FOV (fused2d.cu); two-kernel: the same two kernels as "
+                         "separate calls with the global range")
+    ap.add_argument("--bands", type=int, default=0)
+    ap.add_argument("--graph", action="store_true", help="replay each FOV's pipeline as a captured CUDA graph")
     return ap.parse_args()
 
 
@@ -240,6 +248,15 @@ def run_b200(args):
         cube = cubes[i % len(cubes)]
         st = streams[i % len(streams)] if streams else torch.cuda.current_stream()
         with torch.cuda.stream(st):
+            if args.path == "pipeline":
+                return ops.neighbor2d_pipeline(cube, "F1", bands=args.bands)[0]
+            if args.path == "fused":
+                if ev:
+                    ev[0].record(st)
+                out = ops.neighbor2d_fused(cube, "F1")
+                if ev:
+                    ev[1].record(st)
+                return out
             if ev:
                 ev[0].record(st)
             s, mk = ops.channel_sum(cube, None, normalize=False, dtype=torch.float64, return_max=True)
@@ -261,6 +278,27 @@ def run_b200(args):
     # ---- headline timed region ------------------------------------------------------------------
     for i in range(max(args.warmup, 3)):
         step(i)
+    if args.graph:
+        # one captured graph per resident FOV: the banded pipeline's ~20 stream operations become
+        # a single launch (the pipeline forks to a side stream and joins, which capture follows)
+        torch.cuda.synchronize()
+        graphs, graph_out = [], []
+        for j in range(len(cubes)):
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                graph_out.append(step(j))
+            graphs.append(gr)
+        eager_step = step
+
+        def step(i, ev=None):          # noqa: F811
+            if ev:
+                ev[0].record()
+            graphs[i % len(graphs)].replay()
+            if ev:
+                ev[1].record()
+            return graph_out[i % len(graphs)]
+        for i in range(3):
+            step(i)
     # hold the clocks up: ~0.25 s more of the same work before the timed region (untimed)
     t_end = time.perf_counter() + 0.25
     while time.perf_counter() < t_end:
@@ -282,7 +320,25 @@ def run_b200(args):
     clocks = sampler.stop()
     launches = lib.hipr_launch_count() - launches0
     ms = e0.elapsed_time(e1)
-    k1_ms = sum(a.elapsed_time(b) for a, b in k1_events) / args.steps
+
+    # ---- roofline region: the dominant kernel (channel sum) launched alone, K times ---------------
+    # (inside the headline region its launches share the SMs with the other stream's stencil, so a
+    # per-launch duration taken there would include that overlap)
+    def k1_step(i):
+        return ops.channel_sum(cubes[i % len(cubes)], None, normalize=False, dtype=torch.float64, return_max=True)
+
+    for i in range(3):
+        k1_step(i)
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    r0.record()
+    for i in range(args.steps):
+        k1_step(i)
+    r1.record()
+    barrier()
+    k1_ms = r0.elapsed_time(r1) / args.steps
+    if args.path == "fused":
+        k1_ms = sum(a.elapsed_time(b) for a, b in k1_events) / args.steps
 
     # ---- per-cell spectra region ----------------------------------------------------------------
     def cell_step(i):
@@ -342,11 +398,14 @@ def run_b200(args):
             "metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "flavour": "F1", "patch_size": 11, "phi_range": 9,
+            "config": {"workload": WORKLOAD, "flavour": "F1", "patch_size": 11, "phi_range": 9, "path": args.path,
+                       "streams": args.streams,
                        "l2": "inputs larger than L2 (1.59 GB cube per step, %d FOVs in rotation)" % len(cubes),
                        "arithmetic": "float64 channel sums, 31-bit fixed-point stencil, float32 score"},
             "pipeline_frac_of_hbm_peak": value / world * 1e6 * BYTES_PER_PIXEL / 1e9 / hbm_peak,
-            "roofline": {"bound": "hbm", "kernel": "chansum_bulk_kernel", "achieved": k1_gbs, "peak": hbm_peak,
+            "roofline": {"bound": "hbm", "kernel": "fused2d_kernel" if args.path == "fused" else "chansum_bulk_kernel",
+                         "how": "this kernel launched alone K times between two CUDA events, same inputs",
+                         "share_of_serial_step": k1_ms / (ms / args.steps) if args.streams == 1 else None, "achieved": k1_gbs, "peak": hbm_peak,
                          "unit": "GB/s", "frac": k1_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": npix * BYTES_PER_PIXEL, "ms_per_launch": k1_ms},
             "e2e": {"value": world * npix * e2e_steps / (e2e_dev_ms * 1e-3) / 1e6, "unit": "Mpix/s",

@@ -126,6 +126,67 @@ __device__ __forceinline__ float4 ldg_stream4(const float4 *p) {
                  : "l"(p));
     return v;
 }
+// Sum of C consecutive floats in shared memory, in float64; sixteen loads are issued before the
+// first add so the LDS latency is paid once per batch.
+// PAIRS = false: every channel is converted and added in float64 (the float32 result is then the
+//   correctly rounded sum).  The float->double conversion runs on the XU pipe at 16 lanes/clk/SM:
+//   95 per pixel make XU the busiest pipe of K1 (ncu: 42 %), which K1 can afford (HBM-bound).
+// PAIRS = true: channels are added in pairs in float32 first (one rounding of <= 0.5 ulp of a
+//   ~S/48 partial, ~6e-9 relative on the total), halving the XU work; used by the fused kernel,
+//   whose stencil also needs the XU pipe.
+template <bool PAIRS>
+__device__ __forceinline__ double sum_channels(const float *__restrict__ p, int C) {
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int c = 0;
+    for (; c + 16 <= C; c += 16) {
+        float v[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) v[u] = p[c + u];
+        if (PAIRS) {
+            a0 += (double)(v[0] + v[1]);
+            a1 += (double)(v[2] + v[3]);
+            a2 += (double)(v[4] + v[5]);
+            a3 += (double)(v[6] + v[7]);
+            a0 += (double)(v[8] + v[9]);
+            a1 += (double)(v[10] + v[11]);
+            a2 += (double)(v[12] + v[13]);
+            a3 += (double)(v[14] + v[15]);
+        } else {
+#pragma unroll
+            for (int u = 0; u < 16; u += 4) {
+                a0 += (double)v[u];
+                a1 += (double)v[u + 1];
+                a2 += (double)v[u + 2];
+                a3 += (double)v[u + 3];
+            }
+        }
+    }
+    if (c + 8 <= C) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = p[c + u];
+        if (PAIRS) {
+            a0 += (double)(v[0] + v[1]);
+            a1 += (double)(v[2] + v[3]);
+            a2 += (double)(v[4] + v[5]);
+            a3 += (double)(v[6] + v[7]);
+        } else {
+            a0 += (double)v[0] + (double)v[4];
+            a1 += (double)v[1] + (double)v[5];
+            a2 += (double)v[2] + (double)v[6];
+            a3 += (double)v[3] + (double)v[7];
+        }
+        c += 8;
+    }
+    if (PAIRS) {
+        for (; c + 2 <= C; c += 2) a0 += (double)(p[c] + p[c + 1]);
+        if (c < C) a1 += (double)p[c];
+    } else {
+        for (; c < C; ++c) a0 += (double)p[c];
+    }
+    return (a0 + a1) + (a2 + a3);
+}
+
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));

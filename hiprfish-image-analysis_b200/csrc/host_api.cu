@@ -96,6 +96,7 @@ extern "C" const char *hipr_error_string(int code) {
         case HIPR_E_ALIGN: return "pointer not aligned to its element type";
         case HIPR_E_RANGE: return "size exceeds the index range or the caller's capacity";
         case HIPR_E_NODEVICE: return "no CUDA device";
+        case HIPR_E_UNSUPPORTED: return "request outside this entry point's fast path";
         default: break;
     }
     if (code > 0) return cudaGetErrorString((cudaError_t)code);

@@ -76,13 +76,42 @@ __device__ __forceinline__ float q_reduce(float (&r)[Q_R]) {
 
 template <typename SrcT, int FLAVOUR, bool BAKED>
 __global__ void __launch_bounds__(256)
-lne2d_q_kernel(const SrcT *__restrict__ img, int Hs, int Ws, int64_t ld, int src_off, int H, int W,
+lne2d_q_kernel(const SrcT *__restrict__ img, int Hs, int Ws, int64_t ld, int src_off, int y_begin, int H, int W,
                const __grid_constant__ TableQ tab, const unsigned long long *__restrict__ range,
                float *__restrict__ out) {
     __shared__ float tile[Q_SH * Q_SW];
-    const int x0 = blockIdx.x * Q_TW, y0 = blockIdx.y * Q_TH;
-    const double vmax = double_of_key(range[0]);
-    const double vmin = double_of_key(range[1]);
+    __shared__ double red[16];
+    const int x0 = blockIdx.x * Q_TW, y0 = y_begin + blockIdx.y * Q_TH;
+    double vmax, vmin;
+    if (range != nullptr) {
+        vmax = double_of_key(range[0]);
+        vmin = double_of_key(range[1]);
+    } else {
+        // LOCAL range: F1/F2 are invariant to any affine map, so the tile's own min/max serve (and
+        // give a finer grid); the stencil then does not depend on a global reduction
+        vmax = -__longlong_as_double(0x7ff0000000000000ll);
+        vmin = -vmax;
+        for (int i = threadIdx.x; i < Q_SH * Q_SW; i += 256) {
+            const int ly = i / Q_SW, lx = i - ly * Q_SW;
+            const int sy = min(max(y0 + ly - Q_HALF + src_off, 0), Hs - 1);
+            const int sx = min(max(x0 + lx - Q_HALF + src_off, 0), Ws - 1);
+            const double v = (double)img[(int64_t)sy * ld + sx];
+            vmax = fmax(vmax, v);
+            vmin = fmin(vmin, v);
+        }
+        vmax = warp_max(vmax);
+        vmin = -warp_max(-vmin);
+        if ((threadIdx.x & 31) == 0) {
+            red[(threadIdx.x >> 5) * 2] = vmax;
+            red[(threadIdx.x >> 5) * 2 + 1] = vmin;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            vmax = fmax(vmax, red[2 * j]);
+            vmin = fmin(vmin, red[2 * j + 1]);
+        }
+    }
     const double K = (vmax > vmin) ? Q_SPAN / (vmax - vmin) : 0.0;
     const float eps_q = (K > 0.0) ? (float)(1e-8 * fabs(vmax) * K) : 1.0f;
     for (int i = threadIdx.x; i < Q_SH * Q_SW; i += 256) {
@@ -128,18 +157,20 @@ lne2d_q_kernel(const SrcT *__restrict__ img, int Hs, int Ws, int64_t ld, int src
 }
 
 template <typename SrcT, bool BAKED>
-static int lne2d_q_launch(const SrcT *img, int Hs, int Ws, int64_t ld, int src_off, int H, int W, const TableQ &tab,
-                          int flavour, const unsigned long long *range, float *out, cudaStream_t st) {
-    dim3 grid((W + Q_TW - 1) / Q_TW, (H + Q_TH - 1) / Q_TH);
+static int lne2d_q_launch(const SrcT *img, int Hs, int Ws, int64_t ld, int src_off, int y_begin, int H, int W,
+                          const TableQ &tab, int flavour, const unsigned long long *range, float *out,
+                          cudaStream_t st) {
+    // rows [y_begin, H) of the output are computed
+    dim3 grid((W + Q_TW - 1) / Q_TW, (H - y_begin + Q_TH - 1) / Q_TH);
     switch (flavour) {
         case HIPR_FLAVOUR_F1:
-            lne2d_q_kernel<SrcT, HIPR_FLAVOUR_F1, BAKED><<<grid, 256, 0, st>>>(img, Hs, Ws, ld, src_off, H, W, tab, range, out);
+            lne2d_q_kernel<SrcT, HIPR_FLAVOUR_F1, BAKED><<<grid, 256, 0, st>>>(img, Hs, Ws, ld, src_off, y_begin, H, W, tab, range, out);
             break;
         case HIPR_FLAVOUR_F2:
-            lne2d_q_kernel<SrcT, HIPR_FLAVOUR_F2, BAKED><<<grid, 256, 0, st>>>(img, Hs, Ws, ld, src_off, H, W, tab, range, out);
+            lne2d_q_kernel<SrcT, HIPR_FLAVOUR_F2, BAKED><<<grid, 256, 0, st>>>(img, Hs, Ws, ld, src_off, y_begin, H, W, tab, range, out);
             break;
         case HIPR_FLAVOUR_F3:
-            lne2d_q_kernel<SrcT, HIPR_FLAVOUR_F3, BAKED><<<grid, 256, 0, st>>>(img, Hs, Ws, ld, src_off, H, W, tab, range, out);
+            lne2d_q_kernel<SrcT, HIPR_FLAVOUR_F3, BAKED><<<grid, 256, 0, st>>>(img, Hs, Ws, ld, src_off, y_begin, H, W, tab, range, out);
             break;
         default:
             return HIPR_E_FLAVOUR;
@@ -149,17 +180,16 @@ static int lne2d_q_launch(const SrcT *img, int Hs, int Ws, int64_t ld, int src_o
 
 }  // namespace hipr
 
-using namespace hipr;
-
-extern "C" int hipr_lne2d_q(const void *image_dev, int Hs, int Ws, int64_t ld, int padded, int dtype, int patch_size,
-                            int n_dirs, const int32_t *table_host, int flavour, const uint64_t *range_dev,
-                            float *out_dev, void *stream) {
-    if (!image_dev || !out_dev || !range_dev || !table_host || Hs < 1 || Ws < 1 || ld < Ws) return HIPR_E_ARG;
-    if (dtype != HIPR_F32 && dtype != HIPR_F64) return HIPR_E_DTYPE;
-    if (patch_size != Q_P || n_dirs != Q_R) return HIPR_E_TABLE;   // callers use hipr_lne2d otherwise
+namespace hipr {
+// rows [y_begin, y_end) of the score of an UNPADDED (padded == 0) or padded image; range_dev NULL =
+// tile-local quantisation (F1 / F2 only)
+int lne2d_q_rows(const void *image_dev, int Hs, int Ws, int64_t ld, int padded, int dtype, const int32_t *table_host,
+                 int flavour, const uint64_t *range_dev, float *out_dev, int y_begin, int y_end, cudaStream_t st) {
     const int H = padded ? Hs - (Q_P - 1) : Hs, W = padded ? Ws - (Q_P - 1) : Ws;
     const int src_off = padded ? Q_HALF : 0;
     if (H < 1 || W < 1) return HIPR_E_PATCH;
+    if (y_begin < 0 || y_end > H || y_begin >= y_end) return HIPR_E_ARG;
+    if (!range_dev && flavour != HIPR_FLAVOUR_F1 && flavour != HIPR_FLAVOUR_F2) return HIPR_E_FLAVOUR;
     TableQ tab;
     bool baked = true;
     for (int i = 0; i < Q_R * Q_P; ++i) {
@@ -168,12 +198,26 @@ extern "C" int hipr_lne2d_q(const void *image_dev, int Hs, int Ws, int64_t ld, i
         tab.off[i] = dy * Q_SW + dx;
         baked = baked && dy == kBaked2D[2 * i] && dx == kBaked2D[2 * i + 1];
     }
-    cudaStream_t st = (cudaStream_t)stream;
     const unsigned long long *rg = reinterpret_cast<const unsigned long long *>(range_dev);
     if (dtype == HIPR_F64) {
-        if (baked) return lne2d_q_launch<double, true>((const double *)image_dev, Hs, Ws, ld, src_off, H, W, tab, flavour, rg, out_dev, st);
-        return lne2d_q_launch<double, false>((const double *)image_dev, Hs, Ws, ld, src_off, H, W, tab, flavour, rg, out_dev, st);
+        if (baked) return lne2d_q_launch<double, true>((const double *)image_dev, Hs, Ws, ld, src_off, y_begin, y_end, W, tab, flavour, rg, out_dev, st);
+        return lne2d_q_launch<double, false>((const double *)image_dev, Hs, Ws, ld, src_off, y_begin, y_end, W, tab, flavour, rg, out_dev, st);
     }
-    if (baked) return lne2d_q_launch<float, true>((const float *)image_dev, Hs, Ws, ld, src_off, H, W, tab, flavour, rg, out_dev, st);
-    return lne2d_q_launch<float, false>((const float *)image_dev, Hs, Ws, ld, src_off, H, W, tab, flavour, rg, out_dev, st);
+    if (baked) return lne2d_q_launch<float, true>((const float *)image_dev, Hs, Ws, ld, src_off, y_begin, y_end, W, tab, flavour, rg, out_dev, st);
+    return lne2d_q_launch<float, false>((const float *)image_dev, Hs, Ws, ld, src_off, y_begin, y_end, W, tab, flavour, rg, out_dev, st);
+}
+}  // namespace hipr
+
+using namespace hipr;
+
+extern "C" int hipr_lne2d_q(const void *image_dev, int Hs, int Ws, int64_t ld, int padded, int dtype, int patch_size,
+                            int n_dirs, const int32_t *table_host, int flavour, const uint64_t *range_dev,
+                            float *out_dev, void *stream) {
+    if (!image_dev || !out_dev || !table_host || Hs < 1 || Ws < 1 || ld < Ws) return HIPR_E_ARG;
+    if (dtype != HIPR_F32 && dtype != HIPR_F64) return HIPR_E_DTYPE;
+    if (patch_size != Q_P || n_dirs != Q_R) return HIPR_E_TABLE;   // callers use hipr_lne2d otherwise
+    const int H = padded ? Hs - (Q_P - 1) : Hs;
+    if (H < 1) return HIPR_E_PATCH;
+    return lne2d_q_rows(image_dev, Hs, Ws, ld, padded, dtype, table_host, flavour, range_dev, out_dev, 0, H,
+                        (cudaStream_t)stream);
 }

@@ -25,6 +25,8 @@ _SIGNATURES = {
     "hipr_line_profile_2d": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "hipr_lne2d": (_i, [_vp, _i, _i, _i64, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp]),
     "hipr_lne2d_q": (_i, [_vp, _i, _i, _i64, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp]),
+    "hipr_neighbor2d": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _i, _vp]),
+    "hipr_neighbor2d_fused": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp]),
     "hipr_line_profile_3d": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "hipr_lne3d_dirs": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "hipr_lne3d": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp]),
@@ -70,7 +72,7 @@ def check(code, what):
     if code == 0:
         return
     msg = lib().hipr_error_string(code).decode()
-    if code in (-1, -3, -4, -5, -6, -7):
+    if code in (-1, -3, -4, -5, -6, -7, -9):
         raise ValueError("%s: %s" % (what, msg))
     if code == -2:
         raise TypeError("%s: %s" % (what, msg))

@@ -163,6 +163,62 @@ def lne2d_fixed(image, flavour="F1", patch_size=11, phi_range=9, padded=False, r
     return out
 
 
+UNSUPPORTED = -9
+_SIDE = {}
+
+
+def _side_streams(device, n=2):
+    key = (device.index if device.index is not None else torch.cuda.current_device(), n)
+    if key not in _SIDE:
+        _SIDE[key] = [torch.cuda.Stream(device=device) for _ in range(n)]
+    return _SIDE[key]
+
+
+def neighbor2d_fused(cube, flavour="F1", patch_size=11, phi_range=9, return_sum=False):
+    """cube (H, W, C) float32 -> float32 score in ONE launch (csrc/fused2d.cu).  Returns None when
+    the request is outside the fused kernel's envelope (the caller then uses the two-kernel
+    path).  With return_sum: (score, float64 channel sums, MaxKey)."""
+    cube = _dev(cube, "cube", (torch.float32,))
+    if cube.dim() != 3:
+        raise ValueError("cube must be (H, W, C)")
+    H, W, Cn = cube.shape
+    tab = tables.line_table_2d(patch_size, phi_range)
+    score = torch.empty((H, W), dtype=torch.float32, device=cube.device)
+    s = torch.empty((H, W), dtype=torch.float64, device=cube.device) if return_sum else None
+    mk = MaxKey(cube.device) if return_sum else None
+    with torch.cuda.device(cube.device):
+        code = lib().hipr_neighbor2d_fused(C.c_void_p(cube.data_ptr()), H, W, Cn, tab.shape[1], tab.shape[0],
+                                           _tab_ptr(tab), _flavour(flavour), C.c_void_p(score.data_ptr()),
+                                           C.c_void_p(s.data_ptr()) if return_sum else None,
+                                           mk.ptr() if return_sum else None, _stream())
+    if code == UNSUPPORTED:
+        return None
+    check(code, "neighbor2d_fused")
+    return (score, s, mk) if return_sum else score
+
+
+def neighbor2d_pipeline(cube, flavour="F1", patch_size=11, phi_range=9, bands=0):
+    """cube (H, W, C) float32 -> (score float32, channel sums float64, MaxKey) through
+    hipr_neighbor2d: channel sum and fixed-point stencil overlapped band by band (csrc/pipeline2d.cu).
+    Returns None for parameters outside (11, 9)."""
+    cube = _dev(cube, "cube", (torch.float32,))
+    if cube.dim() != 3:
+        raise ValueError("cube must be (H, W, C)")
+    H, W, Cn = cube.shape
+    tab = tables.line_table_2d(patch_size, phi_range)
+    score = torch.empty((H, W), dtype=torch.float32, device=cube.device)
+    s = torch.empty((H, W), dtype=torch.float64, device=cube.device)
+    mk = MaxKey(cube.device)
+    with torch.cuda.device(cube.device):
+        code = lib().hipr_neighbor2d(C.c_void_p(cube.data_ptr()), H, W, Cn, tab.shape[1], tab.shape[0], _tab_ptr(tab),
+                                     _flavour(flavour), C.c_void_p(score.data_ptr()), C.c_void_p(s.data_ptr()),
+                                     mk.ptr(), int(bands), _stream())
+    if code == UNSUPPORTED:
+        return None
+    check(code, "neighbor2d")
+    return score, s, mk
+
+
 def neighbor2d_score(cube, flavour="F1", calibration=None, patch_size=11, phi_range=9, dtype=None,
                      return_sum=False):
     """cube (H, W, C) or (N, H, W, C) float32 -> score map(s) (H, W) / (N, H, W).
@@ -173,13 +229,38 @@ def neighbor2d_score(cube, flavour="F1", calibration=None, patch_size=11, phi_ra
     type and the floating-point stencil of that type runs, dividing by the max on load."""
     cube = _dev(cube, "cube", (torch.float32,))
     if cube.dim() == 4:
-        res = [neighbor2d_score(c, flavour, None if calibration is None else calibration, patch_size, phi_range,
-                                dtype, return_sum) for c in cube]
+        # independent FOVs alternate between two streams: FOV i+1's channel sum (HBM-bound) runs
+        # under FOV i's stencil (SM-bound); joined on the caller's stream before returning
+        cur = torch.cuda.current_stream(cube.device)
+        side = _side_streams(cube.device)
+        for st in side:
+            st.wait_stream(cur)
+        res = []
+        for i, c in enumerate(cube):
+            with torch.cuda.stream(side[i % len(side)]):
+                res.append(neighbor2d_score(c, flavour, None if calibration is None else calibration, patch_size,
+                                            phi_range, dtype, return_sum))
+        for st in side:
+            cur.wait_stream(st)
+        for r in res:
+            for t in (r if return_sum else (r,)):
+                t.record_stream(cur)
         if return_sum:
             return torch.stack([r[0] for r in res]), torch.stack([r[1] for r in res])
         return torch.stack(res)
     if cube.dim() != 3:
         raise ValueError("cube must be (H, W, C) or (N, H, W, C)")
+    if dtype is None and calibration is None:
+        res = neighbor2d_pipeline(cube, flavour, patch_size, phi_range)
+        if res is not None:
+            score, s, mk = res
+            if not return_sum:
+                return score
+            sn = torch.empty(s.shape, dtype=torch.float32, device=s.device)
+            with torch.cuda.device(cube.device):
+                check(lib().hipr_normalize_cast(C.c_void_p(s.data_ptr()), s.numel(), mk.ptr(),
+                                                C.c_void_p(sn.data_ptr()), _stream()), "normalize_cast")
+            return score, sn
     fixed = dtype is None and tables.line_table_2d(patch_size, phi_range).shape[:2] == (9, 11)
     if dtype is None:
         dtype = torch.float64

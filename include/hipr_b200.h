@@ -51,6 +51,7 @@ extern "C" {
 #define HIPR_E_ALIGN      -6
 #define HIPR_E_RANGE      -7  /* size overflows the kernel's index type */
 #define HIPR_E_NODEVICE   -8
+#define HIPR_E_UNSUPPORTED -9 /* valid request outside this entry point's fast path; use the general one */
 
 #define HIPR_MAX_PATCH     31
 #define HIPR_MAX_TABLE     960   /* n_dirs * patch_size, fits the kernel parameter bank */
@@ -121,11 +122,41 @@ int hipr_lne2d(const void *image_dev, int Hs, int Ws, int64_t ld, int padded, in
  * csrc/lne2d_q.cu).  This is what the cube -> score pipeline uses: image_dev is the float64 (or
  * float32) channel-sum image, range_dev the two keys from hipr_chansum / hipr_image_range; the
  * division by max is implied (the score is invariant to it; F3's epsilon is rescaled).
+ * range_dev NULL (F1 / F2 only): every 32x32 tile is quantised with its own min / max.
  * patch_size must be 11 and n_dirs 9 (HIPR_E_TABLE otherwise: use hipr_lne2d).  out is float32.
  */
 int hipr_lne2d_q(const void *image_dev, int Hs, int Ws, int64_t ld, int padded, int dtype,
                  int patch_size, int n_dirs, const int32_t *table_host, int flavour,
                  const uint64_t *range_dev, float *out_dev, void *stream);
+
+/* ---- the whole 2-D front end in one call, kernels overlapped --------------------------------
+ * cube_dev (H, W, C) float32 -> score_dev (H, W) float32 (same semantics as
+ * hipr_neighbor2d_fused), as row bands: the channel sum of band b+1 (HBM-bound) runs on `stream`
+ * while the fixed-point stencil of band b (SM-bound, tile-local quantisation) runs on an internal
+ * side stream; `stream` is joined before returning control (csrc/pipeline2d.cu).
+ *   sum_dev   (H, W) float64, receives the channel sums (required: it is the intermediate)
+ *   range_dev 2 keys, receive max / min of the sums (reset by this call)
+ *   bands     number of row bands (<= 0: default 1 = the two kernels back to back; banding
+ *             measured slower on B200); F3 always runs unbanded (global epsilon)
+ * patch_size 11 / n_dirs 9 only (HIPR_E_UNSUPPORTED otherwise).
+ */
+int hipr_neighbor2d(const float *cube_dev, int H, int W, int C, int patch_size, int n_dirs,
+                    const int32_t *table_host, int flavour, float *score_dev, double *sum_dev,
+                    uint64_t *range_dev, int bands, void *stream);
+
+/* ---- the whole 2-D front end in one launch -------------------------------------------------
+ * cube_dev (H, W, C) float32 -> score_dev (H, W) float32: channel sum -> [/max] -> edge pad ->
+ * line profiles -> epilogue, i.e. syn/..._measurement.py:105-124 without the skimage denoise
+ * (flavour F1) or the F2 variant (bio/..._analysis.py:665-683).  The sum image stays on chip
+ * (csrc/fused2d.cu).  sum_dev: NULL, or (H, W) float64 that receives the (unnormalised) channel
+ * sums, with range_dev (2 keys, may be NULL) their max / min.
+ * Handles patch_size 11 / 9 directions with the reference's table, flavours F1 and F2, W % 4 == 0,
+ * a 16-byte aligned cube and C up to ~130; anything else returns HIPR_E_UNSUPPORTED and the
+ * caller runs hipr_chansum + hipr_lne2d_q (same arithmetic, two launches).
+ */
+int hipr_neighbor2d_fused(const float *cube_dev, int H, int W, int C, int patch_size, int n_dirs,
+                          const int32_t *table_host, int flavour, float *score_dev,
+                          double *sum_dev, uint64_t *range_dev, void *stream);
 
 /* ---- 3-D stencils -------------------------------------------------------------------------
  * hipr_line_profile_3d replaces line_profile_v2, bio/neighbor.pyx:115-181
