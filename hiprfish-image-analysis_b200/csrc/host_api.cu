@@ -190,7 +190,7 @@ extern "C" int hipr_neighbor2d_host(const float *cube_host, int H, int W, int C,
 extern "C" double hipr_host_last_elapsed_ms(void) { return (double)g_ws.last_ms; }
 
 extern "C" int hipr_cell_spectra_host(const float *cube_host, const void *labels_host, int label_bytes, int64_t npix,
-                                      int C, int64_t capacity, int64_t *n_cells, int64_t *labels_out,
+                                      int64_t row_len, int C, int64_t capacity, int64_t *n_cells, int64_t *labels_out,
                                       int64_t *area_out, double *avgint_out, double *avgint_norm_out) {
     if (!cube_host || !labels_host || !n_cells || !labels_out || !area_out || !avgint_out || !avgint_norm_out ||
         npix < 1 || C < 1 || capacity < 0)
@@ -220,8 +220,14 @@ extern "C" int hipr_cell_spectra_host(const float *cube_host, const void *labels
     HIPR_CUDA(cudaMemsetAsync(w.aux[4], 0, sums_bytes + cnt_bytes + 16, w.comp));
     const int64_t px_bytes = (int64_t)C * 4;
     int64_t band_px = (32ll << 20) / px_bytes;
-    band_px &= ~31ll;  // whole warps' worth of pixels per band
-    if (band_px < 32) band_px = 32;
+    const int64_t W = (row_len > 0 && npix % row_len == 0) ? row_len : npix;
+    if (W < npix) {
+        band_px = (band_px / W) / 32 * 32 * W;   // whole 32-row tiles per band
+        if (band_px < W) band_px = W;
+    } else {
+        band_px &= ~31ll;
+        if (band_px < 32) band_px = 32;
+    }
     if ((e = ws_bands(w, (size_t)band_px * px_bytes))) return e;
     int b = 0;
     for (int64_t p0 = 0; p0 < npix; p0 += band_px, ++b) {
@@ -233,7 +239,8 @@ extern "C" int hipr_cell_spectra_host(const float *cube_host, const void *labels
         HIPR_CUDA(cudaEventRecord(w.copied[slot], w.copy));
         HIPR_CUDA(cudaStreamWaitEvent(w.comp, w.copied[slot], 0));
         if ((e = hipr_cell_spectra_accumulate((const float *)w.band[slot], (const char *)labels_dev + p0 * label_bytes,
-                                              label_bytes, np, C, max_label, sums, counts, nullptr, w.comp)))
+                                              label_bytes, np, (W < npix) ? W : 0, C, max_label, sums, counts, nullptr,
+                                              w.comp)))
             return e;
         HIPR_CUDA(cudaEventRecord(w.freed[slot], w.comp));
     }

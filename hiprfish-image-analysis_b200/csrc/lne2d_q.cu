@@ -82,23 +82,32 @@ lne2d_q_kernel(const SrcT *__restrict__ img, int Hs, int Ws, int64_t ld, int src
     __shared__ float tile[Q_SH * Q_SW];
     __shared__ double red[16];
     const int x0 = blockIdx.x * Q_TW, y0 = y_begin + blockIdx.y * Q_TH;
-    double vmax, vmin;
+    // one pass over the tile: each thread keeps its (at most 7) samples in registers, so the
+    // tile-local range costs no second read
+    constexpr int PER = (Q_SH * Q_SW + 255) / 256;
+    double vals[PER];
+    double vmax = -__longlong_as_double(0x7ff0000000000000ll), vmin = -vmax;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        const int i = threadIdx.x + 256 * k;
+        vals[k] = 0.0;
+        if (i < Q_SH * Q_SW) {
+            const int ly = i / Q_SW, lx = i - ly * Q_SW;
+            const int sy = min(max(y0 + ly - Q_HALF + src_off, 0), Hs - 1);
+            const int sx = min(max(x0 + lx - Q_HALF + src_off, 0), Ws - 1);
+            double v = (double)img[(int64_t)sy * ld + sx];
+            if (v != v) v = 0.0;  // nan_to_num; NaN is not representable in fixed point
+            vals[k] = v;
+            vmax = fmax(vmax, v);
+            vmin = fmin(vmin, v);
+        }
+    }
     if (range != nullptr) {
         vmax = double_of_key(range[0]);
         vmin = double_of_key(range[1]);
     } else {
         // LOCAL range: F1/F2 are invariant to any affine map, so the tile's own min/max serve (and
         // give a finer grid); the stencil then does not depend on a global reduction
-        vmax = -__longlong_as_double(0x7ff0000000000000ll);
-        vmin = -vmax;
-        for (int i = threadIdx.x; i < Q_SH * Q_SW; i += 256) {
-            const int ly = i / Q_SW, lx = i - ly * Q_SW;
-            const int sy = min(max(y0 + ly - Q_HALF + src_off, 0), Hs - 1);
-            const int sx = min(max(x0 + lx - Q_HALF + src_off, 0), Ws - 1);
-            const double v = (double)img[(int64_t)sy * ld + sx];
-            vmax = fmax(vmax, v);
-            vmin = fmin(vmin, v);
-        }
         vmax = warp_max(vmax);
         vmin = -warp_max(-vmin);
         if ((threadIdx.x & 31) == 0) {
@@ -114,15 +123,13 @@ lne2d_q_kernel(const SrcT *__restrict__ img, int Hs, int Ws, int64_t ld, int src
     }
     const double K = (vmax > vmin) ? Q_SPAN / (vmax - vmin) : 0.0;
     const float eps_q = (K > 0.0) ? (float)(1e-8 * fabs(vmax) * K) : 1.0f;
-    for (int i = threadIdx.x; i < Q_SH * Q_SW; i += 256) {
-        const int ly = i / Q_SW, lx = i - ly * Q_SW;
-        int sy = y0 + ly - Q_HALF + src_off, sx = x0 + lx - Q_HALF + src_off;
-        sy = min(max(sy, 0), Hs - 1);
-        sx = min(max(sx, 0), Ws - 1);
-        double v = (double)img[(int64_t)sy * ld + sx];
-        if (v != v) v = 0.0;  // nan_to_num; NaN is not representable in fixed point
-        const double qd = fmin(fmax((v - vmin) * K, 0.0), Q_SPAN);
-        tile[i] = __uint_as_float(__double2uint_rn(qd) + Q_BIAS);
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        const int i = threadIdx.x + 256 * k;
+        if (i < Q_SH * Q_SW) {
+            const double qd = fmin(fmax((vals[k] - vmin) * K, 0.0), Q_SPAN);
+            tile[i] = __uint_as_float(__double2uint_rn(qd) + Q_BIAS);
+        }
     }
     __syncthreads();
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;

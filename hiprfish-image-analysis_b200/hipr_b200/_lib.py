@@ -31,10 +31,11 @@ _SIGNATURES = {
     "hipr_lne3d_dirs": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "hipr_lne3d": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp]),
     "hipr_label_max": (_i, [_vp, _i, _i64, _vp, _vp]),
-    "hipr_cell_spectra_accumulate": (_i, [_vp, _vp, _i, _i64, _i, _i64, _vp, _vp, _vp, _vp]),
+    "hipr_cell_spectra_accumulate": (_i, [_vp, _vp, _i, _i64, _i64, _i, _i64, _vp, _vp, _vp, _vp]),
+    "hipr_cell_spectra_reset": (_i, [_vp, _vp, _i64, _i, _vp]),
     "hipr_cell_spectra_finalize": (_i, [_vp, _vp, _i64, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "hipr_neighbor2d_host": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp]),
-    "hipr_cell_spectra_host": (_i, [_vp, _vp, _i, _i64, _i, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "hipr_cell_spectra_host": (_i, [_vp, _vp, _i, _i64, _i64, _i, _i64, _vp, _vp, _vp, _vp, _vp]),
     "hipr_host_last_elapsed_ms": (C.c_double, []),
     "hipr_host_alloc": (_i, [C.POINTER(_vp), _i64]),
     "hipr_host_free": (_i, [_vp]),

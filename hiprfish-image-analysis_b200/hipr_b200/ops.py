@@ -386,13 +386,20 @@ def cell_spectra_accumulate(cube, labels, max_label, sums=None, counts=None):
     if cube.numel() != npix * Cn:
         raise ValueError("cube %s and labels %s do not match" % (tuple(cube.shape), tuple(labels.shape)))
     max_label = int(max_label)
+    if (sums is None) != (counts is None):
+        raise ValueError("pass both sums and counts (to keep accumulating) or neither")
+    fresh = sums is None
     if sums is None:
-        sums = torch.zeros((max_label + 1, Cn), dtype=torch.float64, device=cube.device)
+        sums = torch.empty((max_label + 1, Cn), dtype=torch.float64, device=cube.device)
     if counts is None:
-        counts = torch.zeros(max_label + 1, dtype=torch.int32, device=cube.device)
+        counts = torch.empty(max_label + 1, dtype=torch.int32, device=cube.device)
     with torch.cuda.device(cube.device):
+        if fresh:
+            check(lib().hipr_cell_spectra_reset(C.c_void_p(sums.data_ptr()), C.c_void_p(counts.data_ptr()), max_label,
+                                                Cn, _stream()), "cell_spectra_reset")
         check(lib().hipr_cell_spectra_accumulate(C.c_void_p(cube.data_ptr()), C.c_void_p(labels.data_ptr()),
-                                                 labels.element_size(), npix, Cn, max_label,
+                                                 labels.element_size(), npix,
+                                                 labels.shape[-1] if labels.dim() > 1 else 0, Cn, max_label,
                                                  C.c_void_p(sums.data_ptr()), C.c_void_p(counts.data_ptr()), None,
                                                  _stream()), "cell_spectra_accumulate")
     return sums, counts
@@ -489,7 +496,8 @@ def cell_spectra_host(cube, labels):
         avg = np.empty((cap, Cn), np.float64)
         norm = np.empty((cap, Cn), np.float64)
         code = lib().hipr_cell_spectra_host(cube.ctypes.data_as(C.c_void_p), labels.ctypes.data_as(C.c_void_p),
-                                            labels.itemsize, npix, Cn, cap, C.byref(n),
+                                            labels.itemsize, npix, labels.shape[-1] if labels.ndim > 1 else 0, Cn, cap,
+                                            C.byref(n),
                                             lab.ctypes.data_as(C.c_void_p), area.ctypes.data_as(C.c_void_p),
                                             avg.ctypes.data_as(C.c_void_p), norm.ctypes.data_as(C.c_void_p))
         if code == -7 and n.value > cap:

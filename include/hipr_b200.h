@@ -184,6 +184,8 @@ int hipr_lne3d(const void *volume_dev, int Xs, int Ys, int Zs, int padded, int d
  * hipr_label_max:   max label (int64, >= 0) of a label image; label_bytes is 4 or 8.
  * hipr_cell_spectra_accumulate:
  *   cube_dev (npix, C) float32; labels_dev (npix) int32/int64, <= 0 = background;
+ *   row_len = length of the label image's fastest axis (W, or Z for volumes), so that the
+ *   kernel can walk 32 x 32 tiles; 0 (or a value that does not divide npix) = flat array;
  *   sums_dev (max_label+1, C) float64 and counts_dev (max_label+1) int32 are ADDED to (zero
  *   them first, or keep accumulating slabs / all-reduce them across ranks); labels above
  *   max_label are counted in *overflow_dev (int32, may be NULL).
@@ -196,9 +198,13 @@ int hipr_lne3d(const void *volume_dev, int Xs, int Ys, int Zs, int padded, int d
 int hipr_label_max(const void *labels_dev, int label_bytes, int64_t npix, int64_t *max_dev,
                    void *stream);
 int hipr_cell_spectra_accumulate(const float *cube_dev, const void *labels_dev,
-                                 int label_bytes, int64_t npix, int C, int64_t max_label,
+                                 int label_bytes, int64_t npix, int64_t row_len, int C,
+                                 int64_t max_label,
                                  double *sums_dev, int32_t *counts_dev, int32_t *overflow_dev,
                                  void *stream);
+/* zero the accumulators (cudaMemsetAsync on `stream`) */
+int hipr_cell_spectra_reset(double *sums_dev, int32_t *counts_dev, int64_t max_label, int C,
+                            void *stream);
 int hipr_cell_spectra_finalize(const double *sums_dev, const int32_t *counts_dev,
                                int64_t max_label, int C, int32_t *n_cells_dev,
                                int64_t *labels_out, int64_t *area_out, double *avgint_out,
@@ -219,7 +225,8 @@ int hipr_neighbor2d_host(const float *cube_host, int H, int W, int C, int patch_
                          int n_dirs, const int32_t *table_host, int flavour,
                          float *score_host, float *sum_host);
 int hipr_cell_spectra_host(const float *cube_host, const void *labels_host, int label_bytes,
-                           int64_t npix, int C, int64_t capacity, int64_t *n_cells,
+                           int64_t npix, int64_t row_len, int C, int64_t capacity,
+                           int64_t *n_cells,
                            int64_t *labels_out, int64_t *area_out, double *avgint_out,
                            double *avgint_norm_out);
 /* device-clock duration (CUDA events: before the first H2D .. after the last D2H) of the most
