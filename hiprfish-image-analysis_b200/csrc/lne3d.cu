@@ -6,8 +6,10 @@
 // shared memory (z fastest, lanes along z: conflict-free), each thread walks TX voxels.  The
 // 792-entry offset table rides in the kernel parameter bank.  This kernel is shared-memory /
 // min-max-ALU bound (792 samples + a 72-value rank selection per voxel), not HBM bound.
+#include <type_traits>
 #include "hipr_common.cuh"
 #include "lne_math.cuh"
+#include "baked_tables.cuh"
 
 namespace hipr {
 
@@ -25,8 +27,36 @@ constexpr int L3_TY = 8, L3_TZ = 32;
 constexpr int L3_SY = L3_TY + L3_P - 1;  // 18
 constexpr int L3_SZ = L3_TZ + L3_P - 1;  // 42
 
+constexpr int l3_baked_off(int t, int li) {
+    return (kBaked3D[(t * L3_P + li) * 3] * L3_SY + kBaked3D[(t * L3_P + li) * 3 + 1]) * L3_SZ +
+           kBaked3D[(t * L3_P + li) * 3 + 2];
+}
+template <int I, int N, typename F>
+__device__ __forceinline__ void l3_static_for(F &&f) {
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        l3_static_for<I + 1, N>(f);
+    }
+}
+// float32 lines use the fast reciprocal divide (2 ulp): one of 72 per voxel, far inside the gate
+template <typename T> __device__ __forceinline__ T l3_div(T a, T b) { return a / b; }
+template <> __device__ __forceinline__ float l3_div<float>(float a, float b) { return __fdividef(a, b); }
+
+template <typename T, int FLAVOUR>
+__device__ __forceinline__ T l3_line_rel(T centre, T mn, T mx, bool bad) {
+    const T range = mx - mn;
+    T r;
+    if (FLAVOUR == HIPR_FLAVOUR_F2) r = l3_div<T>(centre - mn, range);
+    else if (FLAVOUR == HIPR_FLAVOUR_F3) r = l3_div<T>(centre - mn, range + (T)1e-8);
+    else r = l3_div<T>(centre - mn, Num<T>::mx(range, (T)1e-8));
+    if (FLAVOUR != HIPR_FLAVOUR_F2 && bad) r = Num<T>::nan();
+    return r;
+}
+
 // MODE 0: write the 72 per-direction values (me_v2); MODE 1: write the fused score.
-template <typename T, int FLAVOUR, int MODE, int TX>
+// BAKED: the host's table equals the pinned (11, 9, 9) table, whose 792 offsets are then
+// compile-time immediates of the LDS instructions (no table fetch, no address arithmetic).
+template <typename T, int FLAVOUR, int MODE, int TX, bool BAKED>
 __global__ void __launch_bounds__(256)
 lne3d_p11t72_kernel(const T *__restrict__ vol, int Xs, int Ys, int Zs, int src_off, int X, int Y, int Z,
                     const __grid_constant__ Table3D tab,  // (dx * SY + dy) * SZ + dz, patch coords
@@ -62,19 +92,37 @@ lne3d_p11t72_kernel(const T *__restrict__ vol, int Xs, int Ys, int Zs, int src_o
         if (x >= X) break;
         const T *base = tile + (lx * L3_SY + ty) * L3_SZ + tz;
         T r[L3_T];
+        if constexpr (BAKED) {
+            l3_static_for<0, L3_T>([&](auto tc) {
+                constexpr int t = decltype(tc)::value;
+                constexpr int o0 = l3_baked_off(t, 0);
+                T mn = base[o0], mx = mn;
+                bool bad = (mn != mn);
+                l3_static_for<1, L3_P>([&](auto lc) {
+                    constexpr int off = l3_baked_off(t, decltype(lc)::value);
+                    const T s = base[off];
+                    mn = Num<T>::mn(mn, s);
+                    mx = Num<T>::mx(mx, s);
+                    if (FLAVOUR != HIPR_FLAVOUR_F2) bad |= (s != s);
+                });
+                constexpr int oc = l3_baked_off(t, L3_HALF);
+                r[t] = l3_line_rel<T, FLAVOUR>(base[oc], mn, mx, bad);
+            });
+        } else {
 #pragma unroll
-        for (int t = 0; t < L3_T; ++t) {
-            T mn = base[tab.off[t * L3_P]], mx = mn, centre = mn;
-            bool bad = (mn != mn);
+            for (int t = 0; t < L3_T; ++t) {
+                T mn = base[tab.off[t * L3_P]], mx = mn, centre = mn;
+                bool bad = (mn != mn);
 #pragma unroll
-            for (int li = 1; li < L3_P; ++li) {
-                const T s = base[tab.off[t * L3_P + li]];
-                mn = Num<T>::mn(mn, s);
-                mx = Num<T>::mx(mx, s);
-                if (li == L3_HALF) centre = s;
-                if (FLAVOUR != HIPR_FLAVOUR_F2) bad |= (s != s);
+                for (int li = 1; li < L3_P; ++li) {
+                    const T s = base[tab.off[t * L3_P + li]];
+                    mn = Num<T>::mn(mn, s);
+                    mx = Num<T>::mx(mx, s);
+                    if (li == L3_HALF) centre = s;
+                    if (FLAVOUR != HIPR_FLAVOUR_F2) bad |= (s != s);
+                }
+                r[t] = l3_line_rel<T, FLAVOUR>(centre, mn, mx, bad);
             }
-            r[t] = line_rel<T, FLAVOUR>(centre, mn, mx, bad);
         }
         const int64_t v = ((int64_t)x * Y + y) * Z + z;
         if (MODE == 0) {
@@ -83,6 +131,106 @@ lne3d_p11t72_kernel(const T *__restrict__ vol, int Xs, int Ys, int Zs, int src_o
             for (int t = 0; t < L3_T; ++t) o[t] = r[t];
         } else {
             out[v] = reduce_dirs<T, L3_T, FLAVOUR>(r);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Fixed-point variant (see lne2d_q.cu for why): the brick is mapped onto 31-bit integers with the
+// BRICK's own min/max and stored as positive-float bit patterns; min / max / differences along
+// the 72 lines are exact, so float64 channel sums keep their precision at float32 speed and no
+// NaN bookkeeping is needed (NaN samples become 0).  F2 is invariant to the affine map; F3 / ME2
+// carry their 1e-8 into q units with the global max (`maxkey`; NULL = the volume is already
+// normalised).  Baked (11, 9, 9) table only.
+// ---------------------------------------------------------------------------------------
+constexpr uint32_t L3Q_BIAS = 0x00800000u;
+constexpr double L3Q_SPAN = (double)0x7E000000u;
+
+template <typename SrcT, int FLAVOUR, int MODE, int TX>
+__global__ void __launch_bounds__(256)
+lne3d_q_kernel(const SrcT *__restrict__ vol, int Xs, int Ys, int Zs, int src_off, int X, int Y, int Z,
+               const unsigned long long *__restrict__ maxkey, float *__restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw3q[];
+    float *tile = reinterpret_cast<float *>(smem_raw3q);
+    __shared__ double red[16];
+    constexpr int SX = TX + L3_P - 1;
+    const int nzb = (Z + L3_TZ - 1) / L3_TZ;
+    const int z0 = (blockIdx.x % nzb) * L3_TZ;
+    const int y0 = (blockIdx.x / nzb) * L3_TY;
+    const int x0 = blockIdx.y * TX;
+    double bmax = -__longlong_as_double(0x7ff0000000000000ll), bmin = -bmax;
+    for (int i = threadIdx.x; i < SX * L3_SY * L3_SZ; i += 256) {
+        const int lz = i % L3_SZ, rest = i / L3_SZ;
+        const int ly = rest % L3_SY, lx = rest / L3_SY;
+        const int sx = min(max(x0 + lx - L3_HALF + src_off, 0), Xs - 1);
+        const int sy = min(max(y0 + ly - L3_HALF + src_off, 0), Ys - 1);
+        const int sz = min(max(z0 + lz - L3_HALF + src_off, 0), Zs - 1);
+        double v = (double)vol[((int64_t)sx * Ys + sy) * Zs + sz];
+        if (v != v) v = 0.0;
+        bmax = fmax(bmax, v);
+        bmin = fmin(bmin, v);
+    }
+    bmax = warp_max(bmax);
+    bmin = -warp_max(-bmin);
+    if ((threadIdx.x & 31) == 0) {
+        red[(threadIdx.x >> 5) * 2] = bmax;
+        red[(threadIdx.x >> 5) * 2 + 1] = bmin;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        bmax = fmax(bmax, red[2 * j]);
+        bmin = fmin(bmin, red[2 * j + 1]);
+    }
+    const double K = (bmax > bmin) ? L3Q_SPAN / (bmax - bmin) : 0.0;
+    const double gmax = maxkey ? fabs(double_of_key(*maxkey)) : 1.0;
+    const float eps_q = (K > 0.0) ? (float)(1e-8 * gmax * K) : 1.0f;
+    for (int i = threadIdx.x; i < SX * L3_SY * L3_SZ; i += 256) {
+        const int lz = i % L3_SZ, rest = i / L3_SZ;
+        const int ly = rest % L3_SY, lx = rest / L3_SY;
+        const int sx = min(max(x0 + lx - L3_HALF + src_off, 0), Xs - 1);
+        const int sy = min(max(y0 + ly - L3_HALF + src_off, 0), Ys - 1);
+        const int sz = min(max(z0 + lz - L3_HALF + src_off, 0), Zs - 1);
+        double v = (double)vol[((int64_t)sx * Ys + sy) * Zs + sz];   // second read: L1/L2 hit
+        if (v != v) v = 0.0;
+        const double qd = fmin(fmax((v - bmin) * K, 0.0), L3Q_SPAN);
+        tile[i] = __uint_as_float(__double2uint_rn(qd) + L3Q_BIAS);
+    }
+    __syncthreads();
+    const int tz = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int z = z0 + tz, y = y0 + ty;
+    if (z >= Z || y >= Y) return;
+#pragma unroll 1
+    for (int lx = 0; lx < TX; ++lx) {
+        const int x = x0 + lx;
+        if (x >= X) break;
+        const float *base = tile + (lx * L3_SY + ty) * L3_SZ + tz;
+        float r[L3_T];
+        l3_static_for<0, L3_T>([&](auto tc) {
+            constexpr int t = decltype(tc)::value;
+            constexpr int o0 = l3_baked_off(t, 0);
+            float mn = base[o0], mx = mn;
+            l3_static_for<1, L3_P>([&](auto lc) {
+                constexpr int off = l3_baked_off(t, decltype(lc)::value);
+                const float s = base[off];
+                mn = fminf(mn, s);
+                mx = fmaxf(mx, s);
+            });
+            constexpr int oc = l3_baked_off(t, L3_HALF);
+            const float c = base[oc];
+            const float dq = __uint2float_rn(__float_as_uint(c) - __float_as_uint(mn));
+            const float rq = __uint2float_rn(__float_as_uint(mx) - __float_as_uint(mn));
+            if (FLAVOUR == HIPR_FLAVOUR_F2) r[t] = __fdividef(dq, rq);            // 0/0 -> NaN on a flat line
+            else if (FLAVOUR == HIPR_FLAVOUR_F3) r[t] = __fdividef(dq, rq + eps_q);
+            else r[t] = __fdividef(dq, fmaxf(rq, eps_q));
+        });
+        const int64_t v = ((int64_t)x * Y + y) * Z + z;
+        if (MODE == 0) {
+            float *o = out + v * L3_T;
+#pragma unroll
+            for (int t = 0; t < L3_T; ++t) o[t] = r[t];
+        } else {
+            out[v] = reduce_dirs<float, L3_T, FLAVOUR>(r);
         }
     }
 }
@@ -144,13 +292,13 @@ lne3d_generic_kernel(const T *__restrict__ vol, int Xs, int Ys, int Zs, int src_
 
 int upload_offsets(const int *lin, int n, cudaStream_t st, const int **dev_out);
 
-template <typename T, int FLAVOUR, int MODE>
-static int launch_fast3d(const T *vol, int Xs, int Ys, int Zs, int src_off, int X, int Y, int Z, const Table3D &tab,
-                         const unsigned long long *maxkey, T *out, cudaStream_t st) {
+template <typename T, int FLAVOUR, int MODE, bool BAKED>
+static int launch_fast3d_b(const T *vol, int Xs, int Ys, int Zs, int src_off, int X, int Y, int Z, const Table3D &tab,
+                           const unsigned long long *maxkey, T *out, cudaStream_t st) {
     constexpr int TX = (sizeof(T) == 4) ? 8 : 4;
     constexpr int SX = TX + L3_P - 1;
     const size_t smem = (size_t)SX * L3_SY * L3_SZ * sizeof(T);
-    auto kern = lne3d_p11t72_kernel<T, FLAVOUR, MODE, TX>;
+    auto kern = lne3d_p11t72_kernel<T, FLAVOUR, MODE, TX, BAKED>;
     static bool attr_done = false;
     if (!attr_done) {
         HIPR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -161,6 +309,13 @@ static int launch_fast3d(const T *vol, int Xs, int Ys, int Zs, int src_off, int 
     dim3 grid((unsigned)(nzb * nyb), (unsigned)nxb);
     kern<<<grid, 256, smem, st>>>(vol, Xs, Ys, Zs, src_off, X, Y, Z, tab, maxkey, out);
     return after_launch();
+}
+
+template <typename T, int FLAVOUR, int MODE>
+static int launch_fast3d(const T *vol, int Xs, int Ys, int Zs, int src_off, int X, int Y, int Z, const Table3D &tab,
+                         bool baked, const unsigned long long *maxkey, T *out, cudaStream_t st) {
+    if (baked) return launch_fast3d_b<T, FLAVOUR, MODE, true>(vol, Xs, Ys, Zs, src_off, X, Y, Z, tab, maxkey, out, st);
+    return launch_fast3d_b<T, FLAVOUR, MODE, false>(vol, Xs, Ys, Zs, src_off, X, Y, Z, tab, maxkey, out, st);
 }
 
 template <typename T>
@@ -180,14 +335,16 @@ static int lne3d_dispatch(const T *vol, int Xs, int Ys, int Zs, int padded, int 
             if (table[i] < -4 * P || table[i] > 4 * P) return HIPR_E_TABLE;
     if (P == L3_P && Tn == L3_T && in_patch && !flat) {
         Table3D tab;
+        bool baked = true;
         for (int i = 0; i < Tn * P; ++i)
             tab.off[i] = (table[3 * i] * L3_SY + table[3 * i + 1]) * L3_SZ + table[3 * i + 2];
+        for (int i = 0; i < Tn * P * 3; ++i) baked = baked && (table[i] == kBaked3D[i]);
         if (mode == 0)
-            return launch_fast3d<T, HIPR_FLAVOUR_ME2, 0>(vol, Xs, Ys, Zs, src_off, X, Y, Z, tab, maxkey, out, st);
+            return launch_fast3d<T, HIPR_FLAVOUR_ME2, 0>(vol, Xs, Ys, Zs, src_off, X, Y, Z, tab, baked, maxkey, out, st);
         switch (flavour) {
-            case HIPR_FLAVOUR_F2: return launch_fast3d<T, HIPR_FLAVOUR_F2, 1>(vol, Xs, Ys, Zs, src_off, X, Y, Z, tab, maxkey, out, st);
-            case HIPR_FLAVOUR_F3: return launch_fast3d<T, HIPR_FLAVOUR_F3, 1>(vol, Xs, Ys, Zs, src_off, X, Y, Z, tab, maxkey, out, st);
-            case HIPR_FLAVOUR_ME2: return launch_fast3d<T, HIPR_FLAVOUR_ME2, 1>(vol, Xs, Ys, Zs, src_off, X, Y, Z, tab, maxkey, out, st);
+            case HIPR_FLAVOUR_F2: return launch_fast3d<T, HIPR_FLAVOUR_F2, 1>(vol, Xs, Ys, Zs, src_off, X, Y, Z, tab, baked, maxkey, out, st);
+            case HIPR_FLAVOUR_F3: return launch_fast3d<T, HIPR_FLAVOUR_F3, 1>(vol, Xs, Ys, Zs, src_off, X, Y, Z, tab, baked, maxkey, out, st);
+            case HIPR_FLAVOUR_ME2: return launch_fast3d<T, HIPR_FLAVOUR_ME2, 1>(vol, Xs, Ys, Zs, src_off, X, Y, Z, tab, baked, maxkey, out, st);
             default: return HIPR_E_FLAVOUR;
         }
     }
@@ -214,9 +371,62 @@ static int lne3d_dispatch(const T *vol, int Xs, int Ys, int Zs, int padded, int 
     return after_launch();
 }
 
+template <typename SrcT, int FLAVOUR, int MODE>
+static int launch_q3d(const SrcT *vol, int Xs, int Ys, int Zs, int src_off, int X, int Y, int Z,
+                      const unsigned long long *maxkey, float *out, cudaStream_t st) {
+    constexpr int TX = 8;
+    constexpr int SX = TX + L3_P - 1;
+    const size_t smem = (size_t)SX * L3_SY * L3_SZ * sizeof(float);
+    auto kern = lne3d_q_kernel<SrcT, FLAVOUR, MODE, TX>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        HIPR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    const int nzb = (Z + L3_TZ - 1) / L3_TZ, nyb = (Y + L3_TY - 1) / L3_TY, nxb = (X + TX - 1) / TX;
+    if ((int64_t)nzb * nyb > 0x7fffffffLL || nxb > 65535) return HIPR_E_RANGE;
+    dim3 grid((unsigned)(nzb * nyb), (unsigned)nxb);
+    kern<<<grid, 256, smem, st>>>(vol, Xs, Ys, Zs, src_off, X, Y, Z, maxkey, out);
+    return after_launch();
+}
+
+template <typename SrcT>
+static int lne3d_q_dispatch(const SrcT *vol, int Xs, int Ys, int Zs, int padded, int flavour, int mode,
+                            const unsigned long long *maxkey, float *out, cudaStream_t st) {
+    const int P = L3_P;
+    const int X = padded ? Xs - (P - 1) : Xs, Y = padded ? Ys - (P - 1) : Ys, Z = padded ? Zs - (P - 1) : Zs;
+    const int src_off = padded ? L3_HALF : 0;
+    if (X < 1 || Y < 1 || Z < 1) return HIPR_E_PATCH;
+    if (mode == 0) return launch_q3d<SrcT, HIPR_FLAVOUR_ME2, 0>(vol, Xs, Ys, Zs, src_off, X, Y, Z, maxkey, out, st);
+    switch (flavour) {
+        case HIPR_FLAVOUR_F2: return launch_q3d<SrcT, HIPR_FLAVOUR_F2, 1>(vol, Xs, Ys, Zs, src_off, X, Y, Z, maxkey, out, st);
+        case HIPR_FLAVOUR_F3: return launch_q3d<SrcT, HIPR_FLAVOUR_F3, 1>(vol, Xs, Ys, Zs, src_off, X, Y, Z, maxkey, out, st);
+        case HIPR_FLAVOUR_ME2: return launch_q3d<SrcT, HIPR_FLAVOUR_ME2, 1>(vol, Xs, Ys, Zs, src_off, X, Y, Z, maxkey, out, st);
+        default: return HIPR_E_FLAVOUR;
+    }
+}
+
 }  // namespace hipr
 
 using namespace hipr;
+
+// mode 1: fused score (X, Y, Z); mode 0: per-direction values (X, Y, Z, 72).  float32 out.
+extern "C" int hipr_lne3d_q(const void *volume_dev, int Xs, int Ys, int Zs, int padded, int dtype, int patch_size,
+                            int n_dirs, const int32_t *table_host, int flavour, int dirs_only,
+                            const uint64_t *maxkey_dev, float *out_dev, void *stream) {
+    if (!volume_dev || !out_dev || !table_host || Xs < 1 || Ys < 1 || Zs < 1) return HIPR_E_ARG;
+    if (dtype != HIPR_F32 && dtype != HIPR_F64) return HIPR_E_DTYPE;
+    if (patch_size != L3_P || n_dirs != L3_T) return HIPR_E_UNSUPPORTED;
+    for (int i = 0; i < L3_T * L3_P * 3; ++i)
+        if (table_host[i] != kBaked3D[i]) return HIPR_E_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned long long *mk = reinterpret_cast<const unsigned long long *>(maxkey_dev);
+    if (dtype == HIPR_F64)
+        return lne3d_q_dispatch<double>((const double *)volume_dev, Xs, Ys, Zs, padded, flavour, dirs_only ? 0 : 1, mk,
+                                        out_dev, st);
+    return lne3d_q_dispatch<float>((const float *)volume_dev, Xs, Ys, Zs, padded, flavour, dirs_only ? 0 : 1, mk,
+                                   out_dev, st);
+}
 
 extern "C" int hipr_line_profile_3d(const void *volume_padded_dev, int Xp, int Yp, int Zp, int dtype, int patch_size,
                                     int n_dirs, const int32_t *table_host, void *out_dev, void *stream) {

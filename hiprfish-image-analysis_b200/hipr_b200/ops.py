@@ -353,13 +353,41 @@ def lne3d(volume, flavour="F2", patch_size=11, theta_range=9, phi_range=9, padde
     return out
 
 
-def neighbor3d_score(cube, flavour="ME2", patch_size=11, theta_range=9, phi_range=9, dtype=torch.float32):
+def lne3d_fixed(volume, flavour="ME2", patch_size=11, theta_range=9, phi_range=9, padded=False, maxkey=None,
+                dirs_only=False):
+    """lne3d / lne3d_dirs on a 31-bit fixed-point copy of the volume (brick-local range, exact
+    differences; csrc/lne3d.cu).  float32 out.  maxkey scales the 1e-8 epsilons of F3 / ME2 (None: the
+    volume is already normalised).  Returns None outside (11, 9, 9)."""
+    v = _vol(volume, "volume")
+    tab = tables.line_table_3d(patch_size, theta_range, phi_range)
+    T, P = tab.shape[0], tab.shape[1]
+    Xs, Ys, Zs = v.shape
+    dims = [d - P + 1 for d in v.shape] if padded else list(v.shape)
+    if min(dims) < 1:
+        raise ValueError("volume smaller than the patch")
+    out = torch.empty(dims + ([T] if dirs_only else []), dtype=torch.float32, device=v.device)
+    with torch.cuda.device(v.device):
+        code = lib().hipr_lne3d_q(C.c_void_p(v.data_ptr()), Xs, Ys, Zs, int(bool(padded)), _DT[v.dtype], P, T,
+                                  _tab_ptr(tab), _flavour(flavour), int(bool(dirs_only)),
+                                  maxkey.ptr() if maxkey is not None else None, C.c_void_p(out.data_ptr()), _stream())
+    if code == UNSUPPORTED:
+        return None
+    check(code, "lne3d_fixed")
+    return out
+
+
+def neighbor3d_score(cube, flavour="ME2", patch_size=11, theta_range=9, phi_range=9, dtype=None):
     """cube (X, Y, Z, C) float32 -> score volume (X, Y, Z): channel sum -> /max -> edge pad ->
-    3-D line profiles -> epilogue (bio/...analysis.py:807-817 for 'ME2')."""
+    3-D line profiles -> epilogue (bio/...analysis.py:807-817 for 'ME2').  dtype=None: float64 sums +
+    fixed-point stencil (float32 score); torch.float32 / float64: floating-point stencil of that type."""
     cube = _dev(cube, "cube", (torch.float32,))
     if cube.dim() != 4:
         raise ValueError("cube must be (X, Y, Z, C)")
-    s, mk = channel_sum(cube, None, normalize=False, dtype=dtype, return_max=True)
+    s, mk = channel_sum(cube, None, normalize=False, dtype=dtype or torch.float64, return_max=True)
+    if dtype is None:
+        res = lne3d_fixed(s, flavour, patch_size, theta_range, phi_range, padded=False, maxkey=mk)
+        if res is not None:
+            return res
     return lne3d(s, flavour, patch_size, theta_range, phi_range, padded=False, maxkey=mk)
 
 

@@ -178,6 +178,18 @@ int hipr_lne3d(const void *volume_dev, int Xs, int Ys, int Zs, int padded, int d
                int patch_size, int n_dirs, const int32_t *table_host, int flavour,
                const uint64_t *maxkey_dev, void *out_dev, void *stream);
 
+/* Fixed-point 3-D stencil (csrc/lne3d.cu, lne3d_q_kernel): the float64 (or float32) sum volume is
+ * quantised brick by brick onto 31-bit integers, min / max / differences along the lines are
+ * exact; float32 out.  dirs_only != 0: the (X, Y, Z, 72) output of
+ * line_profile_memory_efficient_v2; else the fused score of `flavour` (F2 / F3 / ME2).
+ * maxkey_dev: key of the global max (hipr_chansum) used to scale the 1e-8 epsilons of F3 / ME2;
+ * NULL = the volume is already normalised.  The reference's (11, 9, 9) table only
+ * (HIPR_E_UNSUPPORTED otherwise: use hipr_lne3d).
+ */
+int hipr_lne3d_q(const void *volume_dev, int Xs, int Ys, int Zs, int padded, int dtype,
+                 int patch_size, int n_dirs, const int32_t *table_host, int flavour, int dirs_only,
+                 const uint64_t *maxkey_dev, float *out_dev, void *stream);
+
 /* ---- per-cell mean spectra ----------------------------------------------------------------
  * Replaces the regionprops loop, syn/..._measurement.py:167-172 (eco/...:151-157,
  * ref/...:177-183, bio/..._analysis.py:1214-1220, 1364-1369).

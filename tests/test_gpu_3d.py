@@ -110,3 +110,33 @@ def test_dead_functions_fail_like_the_reference(torch_cuda):
         neighbor.neighbor_average(np.zeros((30, 30, 30), np.float32), 11)
     with pytest.raises(ValueError, match="Buffer dtype mismatch"):
         neighbor.line_profile(np.zeros((12, 12, 12)), 11, 9, 9)
+
+
+@pytest.mark.parametrize("flavour", ["F2", "F3", "ME2"])
+@pytest.mark.parametrize("shape", [(3, 4, 5), (12, 17, 40), (9, 8, 33)])
+def test_lne3d_fixed_point(torch_cuda, oracle, flavour, shape):
+    """Fixed-point 3-D stencil on a float64 (already normalised) volume against the float64 oracle."""
+    import hipr_b200
+    vol = smooth_image(shape, 31).astype(np.float64) + 0.1
+    vol /= vol.max()
+    got = hipr_b200.lne3d_fixed(_cuda(torch_cuda, vol), flavour).cpu().numpy()
+    want = oracle.lne3d(vol, flavour)
+    np.testing.assert_allclose(got, want, rtol=RTOL, atol=5e-7, equal_nan=True)
+
+
+def test_lne3d_fixed_point_dirs_and_pipeline(torch_cuda, oracle):
+    import hipr_b200
+    from hipr_b200 import synth
+    vol = smooth_image((16, 15, 44), 32).astype(np.float64)
+    vol /= vol.max()
+    vp = np.pad(vol, 5, mode="edge")
+    got = hipr_b200.lne3d_fixed(_cuda(torch_cuda, vp), "ME2", padded=True, dirs_only=True).cpu().numpy()
+    want = oracle.line_profile_memory_efficient_v2(vp, 11, 9, 9)
+    np.testing.assert_allclose(got, want, rtol=RTOL, atol=5e-7)
+    cube = synth.make_volume_cube(10, 12, 36, 95, seed=6)
+    s, _ = oracle.prologue(cube.numpy())
+    for fl in ("ME2", "F2", "F3"):
+        got = hipr_b200.neighbor3d_score(cube.cuda(), fl).cpu().numpy()
+        assert got.dtype == np.float32
+        np.testing.assert_allclose(got, oracle.lne3d(s / s.max(), fl), rtol=RTOL, atol=5e-7)
+    assert hipr_b200.lne3d_fixed(_cuda(torch_cuda, vol), "ME2", 7, 5, 4) is None
