@@ -20,6 +20,7 @@ cpu_baseline: the compiled reference Cython (oracle/_ref) + the scripts' numpy b
              on a bounded crop of the same FOV.
 """
 import argparse
+import ctypes
 import json
 import os
 import sys
@@ -58,6 +59,10 @@ def parse():
                          "separate calls with the global range")
     ap.add_argument("--bands", type=int, default=0)
     ap.add_argument("--graph", action="store_true", help="replay each FOV's pipeline as a captured CUDA graph")
+    ap.add_argument("--workload", default="fov", choices=["fov", "mosaic"],
+                    help="fov (default, the headline): one 2048^2 FOV per GPU per step; mosaic: BASELINE config 5, one "
+                         "stitched mosaic split into row slabs across the ranks with an NCCL halo exchange")
+    ap.add_argument("--mosaic-side", type=int, default=16384)
     return ap.parse_args()
 
 
@@ -341,17 +346,23 @@ def run_b200(args):
         k1_ms = sum(a.elapsed_time(b) for a, b in k1_events) / args.steps
 
     # ---- per-cell spectra region ----------------------------------------------------------------
-    import ctypes as C
-    cell_buf = [(torch.empty((m + 1, 95), dtype=torch.float64, device=dev), torch.empty(m + 1, dtype=torch.int32, device=dev))
+    cell_buf = [(torch.empty((m + 1, C), dtype=torch.float64, device=dev), torch.empty(m + 1, dtype=torch.int32, device=dev))
                 for m in max_labels]
 
+    vp = ctypes.c_void_p
+    cell_args = [(vp(cubes[j].data_ptr()), vp(labels[j].data_ptr()), labels[j].element_size(), npix, W, C, max_labels[j],
+                  vp(cell_buf[j][0].data_ptr()), vp(cell_buf[j][1].data_ptr())) for j in range(len(cubes))]
+
     def cell_step(i):
+        # straight through the C ABI (pre-bound arguments): zero the accumulators, then reduce
         j = i % len(cubes)
-        sums, counts = cell_buf[j]
-        # zero the accumulators (cudaMemsetAsync) and reduce: both inside the timed region
-        lib.hipr_cell_spectra_reset(C.c_void_p(sums.data_ptr()), C.c_void_p(counts.data_ptr()), max_labels[j], 95,
-                                    C.c_void_p(torch.cuda.current_stream().cuda_stream))
-        return ops.cell_spectra_accumulate(cubes[j], labels[j], max_labels[j], sums, counts)
+        cube_p, lab_p, lab_b, n_px, row, ch, mlab, sums_p, cnt_p = cell_args[j]
+        st = vp(torch.cuda.current_stream().cuda_stream)
+        lib.hipr_cell_spectra_reset(sums_p, cnt_p, mlab, ch, st)
+        rc = lib.hipr_cell_spectra_accumulate(cube_p, lab_p, lab_b, n_px, row, ch, mlab, sums_p, cnt_p, None, st)
+        if rc:
+            raise RuntimeError("hipr_cell_spectra_accumulate: %d" % rc)
+        return cell_buf[j]
 
     for i in range(3):
         cell_step(i)
@@ -444,10 +455,84 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def run_mosaic(args):
+    """BASELINE config 5: a stitched side x side x 95 mosaic cut into row slabs, one per rank.  Per step:
+    channel sum of the slab -> 5-row halo exchange of the sum image (NCCL send/recv) + all-reduce of its
+    max/min -> fixed-point stencil on the extended slab; then per-cell spectra with an all-reduce of the
+    (L+1, C) partial sums and integer counts.  Extra line, not the headline metric."""
+    import torch
+    import torch.distributed as dist
+    from hipr_b200 import ops, sharding, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world < 2:
+        raise SystemExit("--workload mosaic needs torchrun with >= 2 ranks")
+    dist.init_process_group("nccl", device_id=dev)
+    side = args.mosaic_side
+    r0, r1 = sharding.slab_bounds(side, rank, world)
+    rows = r1 - r0
+    # slab of the synthetic mosaic, generated in 256-row pieces to bound peak memory
+    labels_full_rows, L = synth.make_labels(side, side, seed=4321, device=dev)
+    labels = labels_full_rows[r0:r1].contiguous()
+    del labels_full_rows
+    cube = torch.empty((rows, side, C), dtype=torch.float32, device=dev)
+    for a in range(0, rows, 256):
+        b = min(a + 256, rows)
+        cube[a:b] = synth.make_cube(b - a, side, C, seed=1234 + r0 + a, device=dev, labels=labels[a:b])
+    slab = sharding.MosaicSlab()
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        slab.score(cube, "F1")
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        score = slab.score(cube, "F1")
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    for _ in range(2):
+        slab.cell_spectra(cube, labels, L)
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    c0.record()
+    for _ in range(args.steps):
+        cells = slab.cell_spectra(cube, labels, L)
+    c1.record()
+    barrier()
+    cms = c0.elapsed_time(c1)
+    t = torch.tensor([ms, cms], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, cms = [float(x) for x in t.tolist()]
+    if rank == 0:
+        npix = side * side
+        print(json.dumps({
+            "metric": "mosaic neighbor2d Mpix/s (row slabs + NCCL halo exchange)", "value": npix * args.steps / (ms * 1e-3) / 1e6,
+            "unit": "Mpix/s", "n_gpus": world, "steps": args.steps, "ms_per_step": ms / args.steps, "scaling": "strong",
+            "config": {"workload": "c5: %dx%dx%d mosaic, %d row slabs of %d rows" % (side, side, C, world, rows),
+                       "halo_bytes_per_neighbour": 5 * side * 8, "flavour": "F1"},
+            "frac_of_hbm_peak_per_gpu": npix / world * BYTES_PER_PIXEL / (ms / args.steps * 1e-3) / 1e9 / 6554.2,
+            "cell_spectra": {"cells": int(cells[0].numel()), "ms_per_step": cms / args.steps,
+                             "cells_per_s": int(cells[0].numel()) * args.steps / (cms * 1e-3),
+                             "allreduce_bytes": (L + 1) * (C * 8 + 4)},
+            "score_mean_rank0": float(score.mean())}), flush=True)
+    dist.destroy_process_group()
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "mosaic":
+        run_mosaic(args)
     else:
         run_b200(args)
 

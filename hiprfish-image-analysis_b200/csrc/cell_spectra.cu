@@ -15,7 +15,8 @@
 // tile-based variant with on-chip label slots (8x fewer atomics) was built and measured 2.5x
 // SLOWER: its 120 registers and serial row walk cut the loads in flight; the atomics were never
 // the limit (fire-and-forget REDs).  The grid is exactly one wave of resident CTAs.
-// finalize: one CTA compacts the labels present (ascending) and forms the means.
+// finalize: one CTA compacts the labels present (ascending); a second kernel, one warp per
+// present label, forms the means and their row-max normalisation.
 #include <cstdlib>
 #include "hipr_common.cuh"
 
@@ -131,11 +132,11 @@ label_max_kernel(const LabelT *__restrict__ labels, int64_t npix, unsigned long 
     if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(out, (unsigned long long)m);
 }
 
-// Single CTA: exclusive scan of (count > 0) over labels 1..max_label, then one warp per cell row.
+// Single CTA: exclusive scan of (count > 0) over labels 1..max_label -> the present labels in
+// ascending order (regionprops order) and their pixel counts.
 __global__ void __launch_bounds__(1024)
-cell_finalize_kernel(const double *__restrict__ sums, const int *__restrict__ counts, int64_t max_label, int C,
-                     int *__restrict__ n_cells, long long *__restrict__ labels_out, long long *__restrict__ area_out,
-                     double *__restrict__ avg_out, double *__restrict__ norm_out) {
+cell_compact_kernel(const int *__restrict__ counts, int64_t max_label, int *__restrict__ n_cells,
+                    long long *__restrict__ labels_out, long long *__restrict__ area_out) {
     __shared__ int warp_tot[32];
     __shared__ int carry;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -172,25 +173,35 @@ cell_finalize_kernel(const double *__restrict__ sums, const int *__restrict__ co
         if (tid == 0) carry += warp_tot[31];
         __syncthreads();
     }
-    const int n = carry;
-    if (tid == 0) *n_cells = n;
-    // rows: one warp per cell
-    for (int row = warp; row < n; row += 32) {
+    if (tid == 0) *n_cells = carry;
+}
+
+// One warp per present label: mean spectrum and its row-max normalisation.
+__global__ void __launch_bounds__(256)
+cell_rows_kernel(const double *__restrict__ sums, int C, const int *__restrict__ n_cells,
+                 const long long *__restrict__ labels_out, const long long *__restrict__ area_out,
+                 double *__restrict__ avg_out, double *__restrict__ norm_out) {
+    const int lane = threadIdx.x & 31;
+    const int n = *n_cells;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n; row += nwarps) {
         const long long lab = labels_out[row];
-        const double inv_n = (double)area_out[row];
+        const double npx = (double)area_out[row];
         double mx = -__longlong_as_double(0x7ff0000000000000ll);
         bool anynan = false;
         for (int c = lane; c < C; c += 32) {
-            const double a = sums[lab * C + c] / inv_n;
-            avg_out[(int64_t)row * C + c] = a;
+            const double a = sums[lab * C + c] / npx;
+            avg_out[row * C + c] = a;
             anynan |= (a != a);
             mx = fmax(mx, a);
         }
         mx = warp_max(mx);
         // np.max propagates NaN
         if (__any_sync(0xffffffffu, anynan)) mx = __longlong_as_double(0x7ff8000000000000ll);
-        for (int c = lane; c < C; c += 32)
-            norm_out[(int64_t)row * C + c] = avg_out[(int64_t)row * C + c] / mx;
+        for (int c = lane; c < C; c += 32) {
+            const double a = sums[lab * C + c] / npx;
+            norm_out[row * C + c] = a / mx;
+        }
     }
 }
 
@@ -274,8 +285,16 @@ extern "C" int hipr_cell_spectra_finalize(const double *sums_dev, const int32_t 
     if (!sums_dev || !counts_dev || !n_cells_dev || !labels_out || !area_out || !avgint_out || !avgint_norm_out ||
         C <= 0 || max_label < 0)
         return HIPR_E_ARG;
-    cell_finalize_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(sums_dev, counts_dev, max_label, C, n_cells_dev,
-                                                              (long long *)labels_out, (long long *)area_out,
-                                                              avgint_out, avgint_norm_out);
+    cudaStream_t st = (cudaStream_t)stream;
+    cell_compact_kernel<<<1, 1024, 0, st>>>(counts_dev, max_label, n_cells_dev, (long long *)labels_out,
+                                            (long long *)area_out);
+    int e = after_launch();
+    if (e) return e;
+    int64_t blocks = (max_label + 7) / 8;   // upper bound on the rows: one warp each
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    cell_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(sums_dev, C, n_cells_dev, (const long long *)labels_out,
+                                                       (const long long *)area_out, avgint_out, avgint_norm_out);
     return after_launch();
 }

@@ -26,12 +26,15 @@ constexpr int CS_INFLIGHT_TARGET = 150 * 1024;
 // Otherwise a group can reach a stage's full-barrier one phase early (bulk copies may land out
 // of order), where a parity wait on a phase that has not started passes immediately.
 
-template <typename OutT>
+// CALIB: a second stream, the flat-field divisor (same shape as the cube), lands behind the cube
+// chunk in every stage; consumers add p[c] / q[c] in float64 (syn/..._measurement.py:104-105).
+template <typename OutT, bool CALIB>
 __global__ void __launch_bounds__(CS_MAX_THREADS, 1)
-chansum_bulk_kernel(const float *__restrict__ cube, int64_t nchunks, int C, int cpx, int stages, int groups,
-                    OutT *__restrict__ out, unsigned long long *__restrict__ maxkey) {
+chansum_bulk_kernel(const float *__restrict__ cube, const float *__restrict__ calib, int64_t nchunks, int C, int cpx,
+                    int stages, int groups, OutT *__restrict__ out, unsigned long long *__restrict__ maxkey) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const uint32_t stage_bytes = (uint32_t)cpx * (uint32_t)C * 4u;
+    const uint32_t chunk_bytes = (uint32_t)cpx * (uint32_t)C * 4u;
+    const uint32_t stage_bytes = CALIB ? 2u * chunk_bytes : chunk_bytes;
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);
     uint64_t *empty = full + CS_MAX_STAGES;
     float *ring = reinterpret_cast<float *>(smem_raw + 128);
@@ -57,7 +60,10 @@ chansum_bulk_kernel(const float *__restrict__ cube, int64_t nchunks, int C, int 
                 if (round > 0) mbar_wait(&empty[s], (round - 1) & 1);
                 mbar_expect_tx(&full[s], stage_bytes);
                 bulk_g2s(reinterpret_cast<unsigned char *>(ring) + (size_t)s * stage_bytes,
-                         cube + chunk * (int64_t)cpx * C, stage_bytes, &full[s], pol);
+                         cube + chunk * (int64_t)cpx * C, chunk_bytes, &full[s], pol);
+                if (CALIB)
+                    bulk_g2s(reinterpret_cast<unsigned char *>(ring) + (size_t)s * stage_bytes + chunk_bytes,
+                             calib + chunk * (int64_t)cpx * C, chunk_bytes, &full[s], pol);
                 if (++s == stages) { s = 0; ++round; }
             }
         }
@@ -77,7 +83,7 @@ chansum_bulk_kernel(const float *__restrict__ cube, int64_t nchunks, int C, int 
         mbar_wait(&full[s], parity);
         if (t < cpx) {
             const float *px = ring + (size_t)s * (stage_bytes >> 2) + (size_t)t * C;
-            const double sum = sum_channels<false>(px, C);
+            const double sum = CALIB ? sum_channels_div(px, px + (chunk_bytes >> 2), C) : sum_channels<false>(px, C);
             __syncwarp();
             if ((tid & 31) == 0) mbar_arrive(&empty[s]);
             out[chunk * cpx + t] = (OutT)sum;
@@ -98,7 +104,7 @@ chansum_bulk_kernel(const float *__restrict__ cube, int64_t nchunks, int C, int 
     }
 }
 
-// Generic path (tails, unaligned bases, flat-field divide): one warp per pixel, lanes stride
+// Generic path (tails, unaligned bases): one warp per pixel, lanes stride
 // the channels (coalesced 128-byte requests), float64 butterfly reduction.
 template <typename OutT>
 __global__ void __launch_bounds__(256)
@@ -190,14 +196,15 @@ template <typename OutT>
 static int chansum_launch(const float *cube, const float *calib, int64_t npix, int C, OutT *out,
                           unsigned long long *maxkey, cudaStream_t st) {
     int64_t done = 0;
-    const bool aligned = (((uintptr_t)cube) & 15u) == 0;
-    if (calib == nullptr && aligned) {
+    const bool aligned = (((uintptr_t)cube) & 15u) == 0 && (calib == nullptr || (((uintptr_t)calib) & 15u) == 0);
+    if (aligned) {
+        const int per_px = (calib ? 2 : 1) * C * 4;   // bytes per pixel per stage
         int cpx = 0;
         for (int cand = 128; cand >= 32; cand -= 32) {
-            if ((int64_t)cand * C * 4 * 2 <= CS_INFLIGHT_TARGET) { cpx = cand; break; }
+            if ((int64_t)cand * per_px * 2 <= CS_INFLIGHT_TARGET) { cpx = cand; break; }
         }
         if (cpx > 0 && npix >= cpx) {
-            const int64_t stage_bytes = (int64_t)cpx * C * 4;
+            const int64_t stage_bytes = (int64_t)cpx * per_px;
             int stages = (int)(CS_INFLIGHT_TARGET / stage_bytes);
             if (stages > CS_MAX_STAGES) stages = CS_MAX_STAGES;
             if (stages < 2) stages = 2;
@@ -206,17 +213,26 @@ static int chansum_launch(const float *cube, const float *calib, int64_t npix, i
                 if (stages % gcand == 0) { groups = gcand; break; }
             const int64_t nchunks = npix / cpx;
             const size_t smem = 128 + (size_t)stages * stage_bytes;
-            static bool attr_done[2] = {false, false};
-            auto kern = chansum_bulk_kernel<OutT>;
-            if (!attr_done[sizeof(OutT) == 8]) {
-                HIPR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               CS_SMEM_BUDGET));
-                attr_done[sizeof(OutT) == 8] = true;
-            }
             int64_t grid = sm_count();
             if (grid > nchunks) grid = nchunks;
-            kern<<<(unsigned)grid, groups * CS_GROUP_THREADS + 32, smem, st>>>(cube, nchunks, C, cpx, stages, groups, out,
-                                                                              maxkey);
+            const unsigned threads = groups * CS_GROUP_THREADS + 32;
+            if (calib) {
+                static bool attr_c[2] = {false, false};
+                auto kern = chansum_bulk_kernel<OutT, true>;
+                if (!attr_c[sizeof(OutT) == 8]) {
+                    HIPR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM_BUDGET));
+                    attr_c[sizeof(OutT) == 8] = true;
+                }
+                kern<<<(unsigned)grid, threads, smem, st>>>(cube, calib, nchunks, C, cpx, stages, groups, out, maxkey);
+            } else {
+                static bool attr_n[2] = {false, false};
+                auto kern = chansum_bulk_kernel<OutT, false>;
+                if (!attr_n[sizeof(OutT) == 8]) {
+                    HIPR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM_BUDGET));
+                    attr_n[sizeof(OutT) == 8] = true;
+                }
+                kern<<<(unsigned)grid, threads, smem, st>>>(cube, nullptr, nchunks, C, cpx, stages, groups, out, maxkey);
+            }
             int e = after_launch();
             if (e) return e;
             done = nchunks * cpx;

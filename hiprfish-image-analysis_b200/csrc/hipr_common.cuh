@@ -187,6 +187,31 @@ __device__ __forceinline__ double sum_channels(const float *__restrict__ p, int 
     return (a0 + a1) + (a2 + a3);
 }
 
+// sum_c p[c] / q[c] in float64: the flat-field divide of syn/..._measurement.py:104 followed by the
+// channel sum of :105 (numpy divides in float64, so does this).
+__device__ __forceinline__ double sum_channels_div(const float *__restrict__ p, const float *__restrict__ q, int C) {
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int c = 0;
+    for (; c + 8 <= C; c += 8) {
+        float v[8], w[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            v[u] = p[c + u];
+            w[u] = q[c + u];
+        }
+        a0 += (double)v[0] / (double)w[0];
+        a1 += (double)v[1] / (double)w[1];
+        a2 += (double)v[2] / (double)w[2];
+        a3 += (double)v[3] / (double)w[3];
+        a0 += (double)v[4] / (double)w[4];
+        a1 += (double)v[5] / (double)w[5];
+        a2 += (double)v[6] / (double)w[6];
+        a3 += (double)v[7] / (double)w[7];
+    }
+    for (; c < C; ++c) a0 += (double)p[c] / (double)q[c];
+    return (a0 + a1) + (a2 + a3);
+}
+
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));

@@ -300,3 +300,35 @@ def test_fused_kernel_flat_image(torch_cuda):
     from hipr_b200 import ops
     cube = torch_cuda.full((40, 128, 95), 0.25, device="cuda")
     assert torch_cuda.isnan(ops.neighbor2d_fused(cube, "F1")).all()
+
+
+@pytest.mark.parametrize("C", [95, 63, 32, 130, 300])
+def test_channel_sum_ring_wraps(torch_cuda, C):
+    """Enough chunks per CTA that every stage of the bulk-copy ring is reused several times, for
+    the stage/group geometries the channel count selects (chansum.cu: stages % groups == 0)."""
+    import hipr_b200
+    rng = np.random.default_rng(C)
+    npix = 148 * 128 * 9 + 77          # ~9 chunks per CTA + a ragged tail
+    cube = rng.random((npix, C), dtype=np.float32)
+    want = cube.astype(np.float64).sum(axis=1)
+    got = hipr_b200.channel_sum(_cuda(torch_cuda, cube), normalize=False, dtype=torch_cuda.float64).cpu().numpy()
+    np.testing.assert_allclose(got, want, rtol=1e-14, atol=0)
+
+
+def test_channel_sum_calibration_bulk_path(torch_cuda, oracle):
+    """Flat-field divide fused into the bulk-copy kernel (two streams per stage), ring wrapped."""
+    import hipr_b200
+    rng = np.random.default_rng(77)
+    shape = (420, 512, 95)
+    cube = rng.random(shape, dtype=np.float32)
+    cal = (0.5 + rng.random(shape, dtype=np.float32)).astype(np.float32)
+    got, mk = hipr_b200.channel_sum(_cuda(torch_cuda, cube), _cuda(torch_cuda, cal), normalize=False,
+                                    dtype=torch_cuda.float64, return_max=True)
+    want = (cube.astype(np.float64) / cal.astype(np.float64)).sum(axis=2)
+    np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-14)
+    assert float(mk.value()) == want.max()
+    # and through the pipeline entry point with calibration= (two-kernel path)
+    small = (slice(0, 64), slice(0, 96))
+    score = hipr_b200.neighbor2d_score(_cuda(torch_cuda, cube[small]), "F1", calibration=_cuda(torch_cuda, cal[small]))
+    want_score = oracle.neighbor2d_score(cube[small], "F1", calibration=cal[small])
+    np.testing.assert_allclose(score.cpu().numpy(), want_score, rtol=RTOL, atol=ATOL_FIXED)
