@@ -48,7 +48,10 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--pool", type=int, default=2, help="resident FOVs per GPU that the steps rotate over")
     ap.add_argument("--e2e-steps", type=int, default=0, help="host-buffer steps (0: min(steps, 10))")
-    ap.add_argument("--cpu-sample", type=int, default=1024, help="side of the CPU-baseline crop")
+    ap.add_argument("--cpu-sample", type=int, default=0,
+                    help="side of the CPU crop (0: the whole 2048^2 FOV for the cpu_baseline leg; for --impl reference a "
+                         "side chosen from a calibration pass so that the K timed steps take about --cpu-budget seconds)")
+    ap.add_argument("--cpu-budget", type=float, default=90.0, help="target seconds of the --impl reference timed region")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--streams", type=int, default=2,
                     help="CUDA streams consecutive (independent) FOVs alternate over; 2 lets FOV i+1's channel sum "
@@ -59,10 +62,11 @@ def parse():
                          "separate calls with the global range")
     ap.add_argument("--bands", type=int, default=0)
     ap.add_argument("--graph", action="store_true", help="replay each FOV's pipeline as a captured CUDA graph")
-    ap.add_argument("--workload", default="fov", choices=["fov", "mosaic"],
+    ap.add_argument("--workload", default="fov", choices=["fov", "mosaic", "zstack"],
                     help="fov (default, the headline): one 2048^2 FOV per GPU per step; mosaic: BASELINE config 5, one "
                          "stitched mosaic split into row slabs across the ranks with an NCCL halo exchange")
     ap.add_argument("--mosaic-side", type=int, default=16384)
+    ap.add_argument("--zstack", default="1024x1024x64", help="X x Y x Z of the --workload zstack volume (BASELINE config 4)")
     return ap.parse_args()
 
 
@@ -130,12 +134,24 @@ def run_reference(args):
     for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
         os.environ[k] = "1"          # as syn/Snakefile:13-14
     cores = len(os.sched_getaffinity(0))
-    side = args.cpu_sample
-    # bounded sample: a side x side crop of FOV 0 per step, sized so K steps take minutes at most
-    cube = synth.make_fov(side, side, C, fov_index=0)[0].numpy()
-    _G["cube"] = cube
     _, kind = _lp2d()
     ctx = mp.get_context("fork")
+    side = args.cpu_sample
+    if side <= 0:
+        # bounded sample: calibrate on a 512^2 crop, then pick the crop side (multiple of 64, at most the
+        # whole 2048^2 FOV) whose K timed steps fit --cpu-budget seconds
+        cal = synth.make_fov(512, 512, C, fov_index=0)[0].numpy()
+        _G["cube"] = cal
+        nproc = max(1, min(cores, 512 // 32))
+        with ctx.Pool(nproc) as pool:
+            reference_step(pool, cal, nproc)
+            t0 = time.perf_counter()
+            reference_step(pool, cal, nproc)
+            rate = 512 * 512 / (time.perf_counter() - t0)
+        side = int((rate * args.cpu_budget / max(args.steps + max(args.warmup, 1), 1)) ** 0.5) // 64 * 64
+        side = max(256, min(H, side))
+    cube = synth.make_fov(side, side, C, fov_index=0)[0].numpy()
+    _G["cube"] = cube
     nproc = max(1, min(cores, side // 32))
     with ctx.Pool(nproc) as pool:
         for _ in range(max(args.warmup, 1)):
@@ -441,7 +457,7 @@ def run_b200(args):
             "gpu_launches": launches, "clocks": clocks,
         }
         if not args.no_cpu and world == 1:
-            side = args.cpu_sample
+            side = args.cpu_sample or H
             crop = cubes[0][:side, :side].cpu().numpy()
             for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
                 os.environ[k] = "1"
@@ -527,12 +543,118 @@ def run_mosaic(args):
     dist.destroy_process_group()
 
 
+def run_zstack(args):
+    """BASELINE config 4: one X x Y x Z x 95 z-stack through the 72-direction 3-D stencil, the
+    `generate_3d_segmentation_memory_efficient` chain (bio/..._analysis.py:807-817): channel sum -> /max ->
+    edge pad -> line_profile_memory_efficient_v2 -> mean * (1 - qcv) over the 72 directions.  Extra line, not
+    the headline metric.  With N ranks every rank has its own z-stack (independent volumes, no collective)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import hipr_b200
+    from hipr_b200 import ops, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    X, Y, Z = [int(v) for v in args.zstack.lower().split("x")]
+    cube = torch.empty((X, Y, Z, C), dtype=torch.float32, device=dev)
+    full = synth.make_volume_cube(X, 8, Z, C, seed=99 + rank, device=dev)          # periodic in y with period 8 planes
+    for y in range(0, Y, 8):                                                       # + fresh noise per slab
+        n = min(8, Y - y)
+        cube[:, y:y + n] = full[:, :n] + 0.01 * torch.rand((X, n, Z, 1), device=dev)
+    del full
+    nvox = X * Y * Z
+    lib = hipr_b200.lib()
+
+    def step():
+        return ops.neighbor3d_score(cube, "ME2")
+
+    def k1():
+        return ops.channel_sum(cube, None, normalize=False, dtype=torch.float64, return_max=True)
+
+    for _ in range(max(args.warmup, 3)):
+        score = step()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    l0 = lib.hipr_launch_count()
+    e0.record()
+    for _ in range(args.steps):
+        score = step()
+    e1.record()
+    barrier()
+    launches = lib.hipr_launch_count() - l0
+    ms = e0.elapsed_time(e1) / args.steps
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k1()
+    barrier()
+    r0.record()
+    for _ in range(args.steps):
+        k1()
+    r1.record()
+    barrier()
+    k1_ms = r0.elapsed_time(r1) / args.steps
+    t = torch.tensor([ms, k1_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, k1_ms = [float(v) for v in t.tolist()]
+    if rank == 0:
+        hbm_peak = 6554.2
+        try:
+            hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+        except Exception:
+            pass
+        line = {"metric": "neighbor (3-D) Mvox/s at %dx%dx%dx95ch" % (X, Y, Z), "value": world * nvox / (ms * 1e-3) / 1e6,
+                "unit": "Mvox/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
+                "higher_is_better": True, "scaling": "weak", "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "c4: %dx%dx%dx95 float32 z-stack per GPU, (11, 9, 9) stencil, epilogue ME2" % (X, Y, Z),
+                           "arithmetic": "float64 channel sums, 31-bit fixed-point stencil, float32 score",
+                           "l2": "inputs larger than L2 (%.1f GB cube per step)" % (nvox * C * 4 / 1e9)},
+                "pipeline_frac_of_hbm_peak": nvox * BYTES_PER_PIXEL / (ms * 1e-3) / 1e9 / hbm_peak,
+                "roofline": {"bound": "hbm", "kernel": "chansum_bulk_kernel", "achieved": nvox * BYTES_PER_PIXEL / (k1_ms * 1e-3) / 1e9,
+                             "peak": hbm_peak, "unit": "GB/s", "frac": nvox * BYTES_PER_PIXEL / (k1_ms * 1e-3) / 1e9 / hbm_peak,
+                             "ms_per_launch": k1_ms, "traffic": None},
+                "stencil_ms": ms - k1_ms, "stencil_note": "lne3d_q_kernel is bound by shared-memory loads + FMNMX, not HBM",
+                "gpu_launches": launches, "score_mean": float(score.mean())}
+        if not args.no_cpu and world == 1:
+            # the reference's own 3-D chain on a 32^3 sub-volume (it runs at a few thousand voxels per second)
+            from oracle import hipr_oracle, load_ref
+            ref = load_ref("neighbor")
+            me2 = ref.line_profile_memory_efficient_v2 if ref is not None else hipr_oracle.line_profile_memory_efficient_v2
+            n = 32
+            sub = cube[:n, :n, :n].cpu().numpy()
+            t0 = time.perf_counter()
+            sm = np.sum(sub, axis=3)
+            sm = sm / np.max(sm)
+            dirs = np.asarray(me2(np.pad(sm, 5, mode="edge").astype(np.float64), 11, 9, 9))
+            hipr_oracle.epilogue_F2_dirs(dirs)
+            sec = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": n ** 3 / sec / 1e6, "unit": "Mvox/s", "cores": 1,
+                                    "kind": "reference" if ref is not None else "port",
+                                    "sample": "%d^3 sub-volume through line_profile_memory_efficient_v2 + numpy epilogue, %.1f s" % (n, sec)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
     elif args.workload == "mosaic":
         run_mosaic(args)
+    elif args.workload == "zstack":
+        run_zstack(args)
     else:
         run_b200(args)
 

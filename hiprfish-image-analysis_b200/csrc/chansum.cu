@@ -27,7 +27,10 @@ constexpr int CS_INFLIGHT_TARGET = 150 * 1024;
 // of order), where a parity wait on a phase that has not started passes immediately.
 
 // CALIB: a second stream, the flat-field divisor (same shape as the cube), lands behind the cube
-// chunk in every stage; consumers add p[c] / q[c] in float64 (syn/..._measurement.py:104-105).
+// chunk in every stage; consumers add p[c] / q[c] (syn/..._measurement.py:104-105; sum_channels_div).
+// With twice the bytes and ~3x the arithmetic per pixel, two threads share a pixel (half the channels
+// each, 64-pixel chunks): lanes 2k / 2k+1 read words k*C + c and k*C + 48 + c, which for odd C = 95
+// still fall on 32 distinct banks.
 template <typename OutT, bool CALIB>
 __global__ void __launch_bounds__(CS_MAX_THREADS, 1)
 chansum_bulk_kernel(const float *__restrict__ cube, const float *__restrict__ calib, int64_t nchunks, int C, int cpx,
@@ -71,8 +74,13 @@ chansum_bulk_kernel(const float *__restrict__ cube, const float *__restrict__ ca
     }
 
     // ---- consumers
+    constexpr int TPP = CALIB ? 2 : 1;   // threads per pixel
     const int g = warp / (CS_GROUP_THREADS / 32);
-    const int t = tid - g * CS_GROUP_THREADS;
+    const int t = (tid - g * CS_GROUP_THREADS) / TPP;
+    const int part = (tid - g * CS_GROUP_THREADS) % TPP;
+    const int cper = (C + TPP - 1) / TPP;
+    const int c0 = part * cper;
+    const int cn = (C - c0 < cper) ? (C - c0) : cper;
     double vmax = -__longlong_as_double(0x7ff0000000000000ll);  // -inf
     double vmin = __longlong_as_double(0x7ff0000000000000ll);
     int64_t it = 0;
@@ -82,13 +90,16 @@ chansum_bulk_kernel(const float *__restrict__ cube, const float *__restrict__ ca
         const uint32_t parity = (uint32_t)((it / stages) & 1);
         mbar_wait(&full[s], parity);
         if (t < cpx) {
-            const float *px = ring + (size_t)s * (stage_bytes >> 2) + (size_t)t * C;
-            const double sum = CALIB ? sum_channels_div(px, px + (chunk_bytes >> 2), C) : sum_channels<false>(px, C);
+            const float *px = ring + (size_t)s * (stage_bytes >> 2) + (size_t)t * C + c0;
+            double sum = CALIB ? sum_channels_div(px, px + (chunk_bytes >> 2), cn) : sum_channels<false>(px, cn);
+            if (TPP == 2) sum += __shfl_xor_sync(0xffffffffu, sum, 1);   // cpx % 32 == 0: whole warps take this branch
             __syncwarp();
             if ((tid & 31) == 0) mbar_arrive(&empty[s]);
-            out[chunk * cpx + t] = (OutT)sum;
-            vmax = fmax(vmax, (double)(OutT)sum);
-            vmin = fmin(vmin, (double)(OutT)sum);
+            if (part == 0) {
+                out[chunk * cpx + t] = (OutT)sum;
+                vmax = fmax(vmax, (double)(OutT)sum);
+                vmin = fmin(vmin, (double)(OutT)sum);
+            }
         } else {
             __syncwarp();
             if ((tid & 31) == 0) mbar_arrive(&empty[s]);
@@ -200,7 +211,7 @@ static int chansum_launch(const float *cube, const float *calib, int64_t npix, i
     if (aligned) {
         const int per_px = (calib ? 2 : 1) * C * 4;   // bytes per pixel per stage
         int cpx = 0;
-        for (int cand = 128; cand >= 32; cand -= 32) {
+        for (int cand = calib ? 64 : 128; cand >= 32; cand -= 32) {   // calib: two threads per pixel
             if ((int64_t)cand * per_px * 2 <= CS_INFLIGHT_TARGET) { cpx = cand; break; }
         }
         if (cpx > 0 && npix >= cpx) {

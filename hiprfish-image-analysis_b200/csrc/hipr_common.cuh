@@ -187,10 +187,28 @@ __device__ __forceinline__ double sum_channels(const float *__restrict__ p, int 
     return (a0 + a1) + (a2 + a3);
 }
 
-// sum_c p[c] / q[c] in float64: the flat-field divide of syn/..._measurement.py:104 followed by the
-// channel sum of :105 (numpy divides in float64, so does this).
+// sum_c p[c] / q[c]: the flat-field divide of syn/..._measurement.py:104 followed by the channel sum
+// of :105.  numpy divides in float64; a float64 divide per channel (MUFU.RCP64H + ~10 dependent
+// DFMA) made the kernel latency-bound at a third of the HBM rate, so the quotient is formed as
+//   v / w = v*r0 * (1 + e + e^2 + O(e^3)),  r0 = RCP(w) in float32 (|e| <= ~1.2e-7),  e = 1 - w*r0
+// with v*r0 taken exactly in float64 (two 24-bit significands) and the O(1e-7) correction in
+// float32: the result differs from the correctly rounded quotient by <= ~2e-14 relative (the float32
+// rounding of the correction term), far inside what the fixed-point stencil resolves (4.6e-10 of the
+// image range).  One DFMA, three XU operations and four FFMA per channel.
+__device__ __forceinline__ void div_accum(float v, float w, double &acc, float &corr) {
+    const float r0 = __frcp_rn(w);
+    const float e = fmaf(-w, r0, 1.0f);          // exact up to one rounding of a ~1e-7 quantity
+    if (fabsf(e) < 1e-3f && fabsf(v) < 3.0e38f) {
+        const float pf = v * r0;
+        corr = fmaf(pf, fmaf(e, e, e), corr);
+        acc = fma((double)v, (double)r0, acc);
+    } else {
+        acc += (double)v / (double)w;            // w zero / denormal / non-finite, or v non-finite: numpy's own quotient
+    }
+}
 __device__ __forceinline__ double sum_channels_div(const float *__restrict__ p, const float *__restrict__ q, int C) {
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    float k0 = 0.f, k1 = 0.f, k2 = 0.f, k3 = 0.f;
     int c = 0;
     for (; c + 8 <= C; c += 8) {
         float v[8], w[8];
@@ -199,17 +217,17 @@ __device__ __forceinline__ double sum_channels_div(const float *__restrict__ p, 
             v[u] = p[c + u];
             w[u] = q[c + u];
         }
-        a0 += (double)v[0] / (double)w[0];
-        a1 += (double)v[1] / (double)w[1];
-        a2 += (double)v[2] / (double)w[2];
-        a3 += (double)v[3] / (double)w[3];
-        a0 += (double)v[4] / (double)w[4];
-        a1 += (double)v[5] / (double)w[5];
-        a2 += (double)v[6] / (double)w[6];
-        a3 += (double)v[7] / (double)w[7];
+        div_accum(v[0], w[0], a0, k0);
+        div_accum(v[1], w[1], a1, k1);
+        div_accum(v[2], w[2], a2, k2);
+        div_accum(v[3], w[3], a3, k3);
+        div_accum(v[4], w[4], a0, k0);
+        div_accum(v[5], w[5], a1, k1);
+        div_accum(v[6], w[6], a2, k2);
+        div_accum(v[7], w[7], a3, k3);
     }
-    for (; c < C; ++c) a0 += (double)p[c] / (double)q[c];
-    return (a0 + a1) + (a2 + a3);
+    for (; c < C; ++c) div_accum(p[c], q[c], a0, k0);
+    return ((a0 + a1) + (a2 + a3)) + (double)((k0 + k1) + (k2 + k3));
 }
 
 __device__ __forceinline__ float warp_max(float v) {
