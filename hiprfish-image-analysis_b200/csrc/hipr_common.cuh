@@ -195,16 +195,22 @@ __device__ __forceinline__ double sum_channels(const float *__restrict__ p, int 
 // float32: the result differs from the correctly rounded quotient by <= ~2e-14 relative (the float32
 // rounding of the correction term), far inside what the fixed-point stencil resolves (4.6e-10 of the
 // image range).  One DFMA, three XU operations and four FFMA per channel.
+__device__ __forceinline__ float rcp_approx(float w) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(w));   // one MUFU.RCP, <= 1 ulp
+    return r;
+}
 __device__ __forceinline__ void div_accum(float v, float w, double &acc, float &corr) {
-    const float r0 = __frcp_rn(w);
+    const float r0 = rcp_approx(w);
     const float e = fmaf(-w, r0, 1.0f);          // exact up to one rounding of a ~1e-7 quantity
-    if (fabsf(e) < 1e-3f && fabsf(v) < 3.0e38f) {
-        const float pf = v * r0;
-        corr = fmaf(pf, fmaf(e, e, e), corr);
-        acc = fma((double)v, (double)r0, acc);
-    } else {
-        acc += (double)v / (double)w;            // w zero / denormal / non-finite, or v non-finite: numpy's own quotient
-    }
+    const float pf = v * r0;
+    corr = fmaf(pf, fmaf(e, e, e), corr);
+    acc = fma((double)v, (double)r0, acc);
+}
+static __device__ __noinline__ double sum_channels_div_exact(const float *__restrict__ p, const float *__restrict__ q, int C) {
+    double a = 0.0;
+    for (int c = 0; c < C; ++c) a += (double)p[c] / (double)q[c];
+    return a;
 }
 __device__ __forceinline__ double sum_channels_div(const float *__restrict__ p, const float *__restrict__ q, int C) {
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
@@ -227,7 +233,13 @@ __device__ __forceinline__ double sum_channels_div(const float *__restrict__ p, 
         div_accum(v[7], w[7], a3, k3);
     }
     for (; c < C; ++c) div_accum(p[c], q[c], a0, k0);
-    return ((a0 + a1) + (a2 + a3)) + (double)((k0 + k1) + (k2 + k3));
+    const double total = ((a0 + a1) + (a2 + a3)) + (double)((k0 + k1) + (k2 + k3));
+    // A divisor that is zero, denormal (flushed) or non-finite, or a non-finite numerator, makes r0 or e
+    // infinite / NaN and therefore the total non-finite: that pixel is redone with numpy's own float64
+    // quotients, channel by channel (never taken on real flat fields).  A divisor above 2^126 has its
+    // reciprocal flushed to zero: the term becomes 0 instead of ~v * 1e-38.
+    if (!(fabs(total) < 1.7e308)) return sum_channels_div_exact(p, q, C);
+    return total;
 }
 
 __device__ __forceinline__ float warp_max(float v) {
