@@ -16,6 +16,7 @@ _SIGNATURES = {
     "hipr_launch_count": (_i64, []),
     "hipr_sm_count": (_i, []),
     "hipr_chansum": (_i, [_vp, _vp, _i64, _i, _vp, _i, _vp, _vp]),
+    "hipr_register_stacks": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "hipr_image_range": (_i, [_vp, _i, _i64, _vp, _vp]),
     "hipr_normalize_cast": (_i, [_vp, _i64, _vp, _vp, _vp]),
     "hipr_normalize": (_i, [_vp, _i, _i64, _vp, _vp]),

@@ -3,6 +3,7 @@ torch's current stream.  torch is used for device memory and streams only; every
 runs here is one of libhipr_b200's.  No CPU fallback: CPU tensors are rejected.
 
 Reference blocks replaced (paths relative to the reference repository):
+  register_stacks   syn/hiprfish_imaging_multispecies_spectral_image_measurement.py:86-105
   channel_sum       syn/hiprfish_imaging_multispecies_spectral_image_measurement.py:105-106
   lne2d             eco/neighbor2d.pyx:56-63 + syn/...measurement.py:109-124 (F1), bio F2 / F3
   neighbor2d_score  syn/...measurement.py:105-124 without the skimage denoise
@@ -103,6 +104,55 @@ def channel_sum(cube, calibration=None, normalize=True, dtype=torch.float32, ret
             check(lib().hipr_normalize(C.c_void_p(out.data_ptr()), _DT[dtype], npix, mk.ptr(), _stream()),
                   "normalize")
     return (out, mk) if return_max else out
+
+
+def register_stacks(stacks, shifts=None, calibration=None, return_cube=True):
+    """Registration paste + np.dstack + flat-field divide + channel sum in one pass (csrc/register.cu).
+
+    stacks: list of (H, W, c_e) float32 CUDA tensors, one per excitation; shifts: per stack (row, col)
+    integer shifts as the scripts derive them from register_translation (int(shift_vector)), None = no
+    shift; calibration: None or a (H, W, C) float32 divisor.  Returns (cube (H, W, C) float32 or None,
+    channel sums (H, W) float64, MaxKey)."""
+    stacks = [_dev(s, "stack %d" % i, (torch.float32,)) for i, s in enumerate(stacks)]
+    if not stacks:
+        raise ValueError("need at least one excitation stack")
+    H, W = stacks[0].shape[:2]
+    for s in stacks:
+        if s.dim() != 3 or tuple(s.shape[:2]) != (H, W):
+            raise ValueError("every stack must be (H, W, c_e) with the same H, W")
+    n = len(stacks)
+    if shifts is None:
+        shifts = [(0, 0)] * n
+    if len(shifts) != n:
+        raise ValueError("one (row, col) shift per stack")
+    chans = np.asarray([s.shape[2] for s in stacks], dtype=np.int32)
+    srow = np.asarray([int(v[0]) for v in shifts], dtype=np.int32)     # int(): truncation, as the scripts do
+    scol = np.asarray([int(v[1]) for v in shifts], dtype=np.int32)
+    Cn = int(chans.sum())
+    dev = stacks[0].device
+    if calibration is not None:
+        calibration = _dev(calibration, "calibration", (torch.float32,))
+        if tuple(calibration.shape) != (H, W, Cn):
+            calibration = calibration.expand(H, W, Cn).contiguous()
+    cube = torch.empty((H, W, Cn), dtype=torch.float32, device=dev) if return_cube else None
+    s64 = torch.empty((H, W), dtype=torch.float64, device=dev)
+    mk = MaxKey(dev)
+    ptrs = (C.c_void_p * n)(*[s.data_ptr() for s in stacks])
+    with torch.cuda.device(dev):
+        check(lib().hipr_register_stacks(ptrs, chans.ctypes.data_as(C.c_void_p), srow.ctypes.data_as(C.c_void_p),
+                                         scol.ctypes.data_as(C.c_void_p), n, H, W,
+                                         C.c_void_p(calibration.data_ptr()) if calibration is not None else None,
+                                         C.c_void_p(cube.data_ptr()) if cube is not None else None,
+                                         C.c_void_p(s64.data_ptr()), mk.ptr(), _stream()), "register_stacks")
+    return cube, s64, mk
+
+
+def neighbor2d_score_from_stacks(stacks, shifts=None, calibration=None, flavour="F1", return_cube=True):
+    """syn/..._measurement.py:86-124 without the skimage calls: excitation stacks -> registered cube,
+    channel sums, score map (fixed-point stencil).  Returns (score, cube, sums, MaxKey)."""
+    cube, s64, mk = register_stacks(stacks, shifts, calibration, return_cube)
+    score = lne2d_fixed(s64, flavour, 11, 9, padded=False, range_keys=mk)
+    return score, cube, s64, mk
 
 
 def lne2d(image, flavour="F1", patch_size=11, phi_range=9, padded=False, maxkey=None):

@@ -77,6 +77,24 @@ int         hipr_sm_count(void);
 int hipr_chansum(const float *cube_dev, const float *calib_dev, int64_t npix, int C,
                  void *sum_dev, int sum_dtype, uint64_t *maxkey_dev, void *stream);
 
+/* ---- registration paste + channel stack + flat field + channel sum, one pass --------------------
+ * Replaces syn/..._measurement.py:86-105 (bio/..._analysis.py:330-348; eco/..._measurement.py:147-148
+ * with zero shifts): the per-excitation images are pasted at their integer registration shifts
+ *   registered_e[r, c, :] = stack_e[r - shift_row[e], c - shift_col[e], :]      (0 where that falls outside)
+ * stacked along the channel axis (np.dstack), divided by the flat field, and channel-summed.
+ *   stacks_dev  HOST array of n_stacks device pointers, stack e is (H, W, chans[e]) float32
+ *   chans, shift_row, shift_col   HOST int32 arrays of length n_stacks (<= 8; sum of chans <= 192)
+ *   calib_dev   NULL, or (H, W, C) float32 divisor, C = sum(chans)
+ *   cube_dev    NULL, or (H, W, C) float32: receives the registered (and flat-fielded) cube, the
+ *               `image_registered` the scripts save and run the per-cell reduction on
+ *   sum_dev     (H, W) float64 channel sums of the registered, flat-fielded cube
+ *   maxkey_dev  NULL or two keys (max, min of the sums), as hipr_chansum
+ * The shifts themselves come from the caller (skimage.feature.register_translation is out of scope).
+ */
+int hipr_register_stacks(const float *const *stacks_dev, const int32_t *chans, const int32_t *shift_row,
+                         const int32_t *shift_col, int n_stacks, int H, int W, const float *calib_dev,
+                         float *cube_dev, double *sum_dev, uint64_t *maxkey_dev, void *stream);
+
 /* global min / max of any image as keys: range_dev[0] = max key, range_dev[1] = min key */
 int hipr_image_range(const void *image_dev, int dtype, int64_t n, uint64_t *range_dev, void *stream);
 /* out_dev[i] = (float)(sum_dev[i] / max), out of place from a float64 sum image

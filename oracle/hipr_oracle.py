@@ -229,6 +229,33 @@ def prologue(cube, calibration=None, normalize=True, pad=5, sum_axes=None):
     return s, np.pad(sn, pad, mode="edge").astype(np.float64)
 
 
+def register_stacks(image_stack, shift_vectors, calibration_image=None):
+    """Registration paste, channel stack, flat field, channel sum:
+    syn/hiprfish_imaging_multispecies_spectral_image_measurement.py:86-105 (test infrastructure).
+    shift_vectors: per stack (row, col), truncated with int() as at :89-90.  The reference uses
+    image_stack[0].shape[0] for both axes (:87, square images); here rows use H and columns W, the same
+    thing on square images.  Returns (image_channel (H, W, C) float64, image_registered_sum (H, W))."""
+    image_registered = [np.zeros(image.shape) for image in image_stack]
+    H, W = image_stack[0].shape[:2]
+    for i in range(len(image_stack)):
+        shift_row = int(shift_vectors[i][0])
+        shift_col = int(shift_vectors[i][1])
+        original_row_min = int(np.maximum(0, shift_row))
+        original_row_max = int(H + np.minimum(0, shift_row))
+        original_col_min = int(np.maximum(0, shift_col))
+        original_col_max = int(W + np.minimum(0, shift_col))
+        registered_row_min = int(-np.minimum(0, shift_row))
+        registered_row_max = int(H - np.maximum(0, shift_row))
+        registered_col_min = int(-np.minimum(0, shift_col))
+        registered_col_max = int(W - np.maximum(0, shift_col))
+        image_registered[i][original_row_min: original_row_max, original_col_min: original_col_max, :] = \
+            image_stack[i][registered_row_min: registered_row_max, registered_col_min: registered_col_max, :]
+    image_channel = np.dstack(image_registered)
+    if calibration_image is not None:
+        image_channel = image_channel / calibration_image
+    return image_channel, np.sum(image_channel, axis=2)
+
+
 def _mean_quartiles(rnc, axis):
     m = np.average(rnc, axis=axis)
     with np.errstate(invalid="ignore"):

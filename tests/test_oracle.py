@@ -119,3 +119,26 @@ def test_reference_errors(ref2d, ref3d):
         ref2d.line_profile_2d_v2(np.zeros((12, 12), np.float32), 11, 9)
     with pytest.raises(ValueError, match="Buffer dtype mismatch"):
         ref3d.neighbor_average(np.zeros((30, 30, 30), np.float32), 11)
+
+
+def test_register_stacks_is_a_shifted_paste(oracle):
+    """oracle.register_stacks (syn/..._measurement.py:86-105) == out[r, c] = in[r - sr, c - sc], zero outside."""
+    rng = np.random.default_rng(0)
+    H, W = 13, 13
+    stacks = [rng.random((H, W, c)) for c in (3, 2, 4)]
+    shifts = [(0, 0), (2.7, -3.2), (-5, 1)]
+    cube, s = oracle.register_stacks(stacks, shifts)
+    want = np.zeros((H, W, 9))
+    off = 0
+    for a, (sr, sc) in zip(stacks, shifts):
+        sr, sc = int(sr), int(sc)
+        for r in range(H):
+            for c in range(W):
+                if 0 <= r - sr < H and 0 <= c - sc < W:
+                    want[r, c, off:off + a.shape[2]] = a[r - sr, c - sc]
+        off += a.shape[2]
+    assert np.array_equal(cube, want)
+    assert np.array_equal(s, want.sum(axis=2))
+    cal = 0.5 + rng.random((H, W, 9))
+    cube2, s2 = oracle.register_stacks(stacks, shifts, cal)
+    assert np.array_equal(cube2, want / cal) and np.array_equal(s2, (want / cal).sum(axis=2))
