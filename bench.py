@@ -222,6 +222,25 @@ class ClockSampler(threading.Thread):
                 "samples": len(s)}
 
 
+def bind_to_gpu_cpus(index):
+    """Pins this process to the CPUs NVML reports as local to GPU `index` (its NUMA node), so that the pinned
+    host buffers of the end-to-end leg are allocated next to the GPU's PCIe root port.  Best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        allowed = os.sched_getaffinity(0)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        ideal = {64 * i + b for i, wd in enumerate(words) for b in range(64) if (wd >> b) & 1}
+        cpus = ideal & allowed
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return "%d of %d allowed cpus" % (len(cpus), len(allowed))
+    except Exception as exc:      # NVML or the cpuset may not allow it: run unbound
+        return "unbound (%s)" % type(exc).__name__
+    return "unbound"
+
+
 # ------------------------------------------------------------------------------------------------
 # the CUDA arm
 # ------------------------------------------------------------------------------------------------
@@ -240,6 +259,7 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_cpus(local)       # before any pinned allocation: host buffers land on the GPU's NUMA node
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -410,14 +430,27 @@ def run_b200(args):
     torch.cuda.synchronize()
     e2e_wall_ms = 1e3 * (time.perf_counter() - t0)
     score_check = float(score_host.mean())
+    # the same FOV as the uint16 counts a detector delivers (value = count / 65535 in float32, bioformats' rescale)
+    raw = ops.pinned_empty((H, W, C), np.uint16)
+    cmax = float(cubes[0].max())
+    torch.from_numpy(raw.view(np.int16)).copy_((cubes[0] * (0.9 * 65535.0 / cmax)).round().to(torch.int32).cpu().to(torch.int16))
+    for _ in range(2):
+        ops.neighbor2d_score_host_raw(raw, 65535.0, "F1", out=score_host)
+    barrier()
+    raw_dev_ms = 0.0
+    for _ in range(e2e_steps):
+        ops.neighbor2d_score_host_raw(raw, 65535.0, "F1", out=score_host)
+        raw_dev_ms += lib.hipr_host_last_elapsed_ms()
+    torch.cuda.synchronize()
+    del raw
 
     # ---- reduce over ranks (max time) -----------------------------------------------------------
-    t = torch.tensor([ms, cell_ms, e2e_dev_ms, e2e_wall_ms, k1_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, cell_ms, e2e_dev_ms, e2e_wall_ms, k1_ms, raw_dev_ms], dtype=torch.float64, device=dev)
     cnt = torch.tensor([launches, cells_per_step], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    ms, cell_ms, e2e_dev_ms, e2e_wall_ms, k1_ms = [float(x) for x in t.tolist()]
+    ms, cell_ms, e2e_dev_ms, e2e_wall_ms, k1_ms, raw_dev_ms = [float(x) for x in t.tolist()]
     launches, cells_all = int(cnt[0].item()), float(cnt[1].item())
 
     if rank == 0:
@@ -445,7 +478,13 @@ def run_b200(args):
             "e2e": {"value": world * npix * e2e_steps / (e2e_dev_ms * 1e-3) / 1e6, "unit": "Mpix/s",
                     "h2d_bytes_per_step": npix * C * 4, "d2h_bytes_per_step": npix * 4, "steps": e2e_steps,
                     "ms_per_step": e2e_dev_ms / e2e_steps, "wall_ms_per_step": e2e_wall_ms / e2e_steps,
-                    "api": "hipr_neighbor2d_host (C ABI, pinned host buffers)", "score_mean": score_check},
+                    "api": "hipr_neighbor2d_host (C ABI, pinned host buffers)", "score_mean": score_check,
+                    "host_numa_binding": numa},
+            "e2e_raw_u16": {"value": world * npix * e2e_steps / (raw_dev_ms * 1e-3) / 1e6, "unit": "Mpix/s",
+                            "h2d_bytes_per_step": npix * C * 2, "d2h_bytes_per_step": npix * 4,
+                            "ms_per_step": raw_dev_ms / e2e_steps,
+                            "api": "hipr_neighbor2d_host_raw: the FOV as the detector's uint16 counts, rescaled on the "
+                                   "GPU exactly as bioformats does on the host (half the PCIe bytes, same score)"},
             "cell_spectra": {"cells_per_s": cells_all * args.steps / (cell_ms * 1e-3),
                              "mpix_per_s": world * npix * args.steps / (cell_ms * 1e-3) / 1e6,
                              "ms_per_step": cell_ms / args.steps, "cells_per_fov": cells_all / world,

@@ -32,16 +32,19 @@ constexpr int CS_INFLIGHT_TARGET = 150 * 1024;
 // With twice the bytes and ~3x the arithmetic per pixel, two threads share a pixel (half the channels
 // each, 64-pixel chunks): lanes 2k / 2k+1 read words k*C + c and k*C + 48 + c, which for odd C = 95
 // still fall on 32 distinct banks.
-template <typename OutT, bool CALIB>
+// InT: float, or raw detector counts (uint16_t / uint8_t) converted on the fly as python-bioformats'
+// rescale does, float32(count) / float32(scale) per sample (raw_value); half / a quarter of the bytes.
+template <typename OutT, bool CALIB, typename InT>
 __global__ void __launch_bounds__(CS_MAX_THREADS, 1)
-chansum_bulk_kernel(const float *__restrict__ cube, const float *__restrict__ calib, int64_t nchunks, int C, int cpx,
-                    int stages, int groups, OutT *__restrict__ out, unsigned long long *__restrict__ maxkey) {
+chansum_bulk_kernel(const InT *__restrict__ cube, const float *__restrict__ calib, int64_t nchunks, int C, int cpx,
+                    int stages, int groups, float scale, OutT *__restrict__ out,
+                    unsigned long long *__restrict__ maxkey) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const uint32_t chunk_bytes = (uint32_t)cpx * (uint32_t)C * 4u;
+    const uint32_t chunk_bytes = (uint32_t)cpx * (uint32_t)C * (uint32_t)sizeof(InT);
     const uint32_t stage_bytes = CALIB ? 2u * chunk_bytes : chunk_bytes;
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);
     uint64_t *empty = full + CS_MAX_STAGES;
-    float *ring = reinterpret_cast<float *>(smem_raw + 128);
+    unsigned char *ring = smem_raw + 128;
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
@@ -63,11 +66,10 @@ chansum_bulk_kernel(const float *__restrict__ cube, const float *__restrict__ ca
             for (int64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
                 if (round > 0) mbar_wait(&empty[s], (round - 1) & 1);
                 mbar_expect_tx(&full[s], stage_bytes);
-                bulk_g2s(reinterpret_cast<unsigned char *>(ring) + (size_t)s * stage_bytes,
-                         cube + chunk * (int64_t)cpx * C, chunk_bytes, &full[s], pol);
+                bulk_g2s(ring + (size_t)s * stage_bytes, cube + chunk * (int64_t)cpx * C, chunk_bytes, &full[s], pol);
                 if (CALIB)
-                    bulk_g2s(reinterpret_cast<unsigned char *>(ring) + (size_t)s * stage_bytes + chunk_bytes,
-                             calib + chunk * (int64_t)cpx * C, chunk_bytes, &full[s], pol);
+                    bulk_g2s(ring + (size_t)s * stage_bytes + chunk_bytes, calib + chunk * (int64_t)cpx * C,
+                             chunk_bytes, &full[s], pol);
                 if (++s == stages) { s = 0; ++round; }
             }
         }
@@ -91,8 +93,14 @@ chansum_bulk_kernel(const float *__restrict__ cube, const float *__restrict__ ca
         const uint32_t parity = (uint32_t)((it / stages) & 1);
         mbar_wait(&full[s], parity);
         if (t < cpx) {
-            const float *px = ring + (size_t)s * (stage_bytes >> 2) + (size_t)t * C + c0;
-            double sum = CALIB ? sum_channels_div(px, px + (chunk_bytes >> 2), cn) : sum_channels<false>(px, cn);
+            const InT *px = reinterpret_cast<const InT *>(ring + (size_t)s * stage_bytes) + (size_t)t * C + c0;
+            double sum;
+            if constexpr (CALIB)
+                sum = sum_channels_div(px, px + (chunk_bytes >> 2), cn);
+            else if constexpr (sizeof(InT) == 4)
+                sum = sum_channels<false>(px, cn);
+            else
+                sum = sum_channels_raw(px, cn, scale);
             if (TPP == 2) sum += __shfl_xor_sync(0xffffffffu, sum, 1);   // cpx % 32 == 0: whole warps take this branch
             __syncwarp();
             if ((tid & 31) == 0) mbar_arrive(&empty[s]);
@@ -118,10 +126,10 @@ chansum_bulk_kernel(const float *__restrict__ cube, const float *__restrict__ ca
 
 // Generic path (tails, unaligned bases): one warp per pixel, lanes stride
 // the channels (coalesced 128-byte requests), float64 butterfly reduction.
-template <typename OutT>
+template <typename OutT, typename InT>
 __global__ void __launch_bounds__(256)
-chansum_warp_kernel(const float *__restrict__ cube, const float *__restrict__ calib, int64_t p0,
-                    int64_t p1, int C, OutT *__restrict__ out,
+chansum_warp_kernel(const InT *__restrict__ cube, const float *__restrict__ calib, int64_t p0,
+                    int64_t p1, int C, float scale, OutT *__restrict__ out,
                     unsigned long long *__restrict__ maxkey) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -129,9 +137,11 @@ chansum_warp_kernel(const float *__restrict__ cube, const float *__restrict__ ca
     double vmax = -__longlong_as_double(0x7ff0000000000000ll);
     double vmin = __longlong_as_double(0x7ff0000000000000ll);
     for (int64_t p = p0 + warp0; p < p1; p += nwarps) {
-        const float *px = cube + p * C;
+        const InT *px = cube + p * C;
         double a = 0.0;
-        if (calib == nullptr) {
+        if constexpr (sizeof(InT) != 4) {
+            for (int c = lane; c < C; c += 32) a += (double)raw_value(px[c], scale);
+        } else if (calib == nullptr) {
             for (int c = lane; c < C; c += 32) a += (double)ldg_stream(px + c);
         } else {
             const float *cl = calib + p * C;
@@ -204,13 +214,13 @@ __global__ void range_encode_kernel(const double *__restrict__ v, unsigned long 
     k[1] = key_of_double(v[1]);
 }
 
-template <typename OutT>
-static int chansum_launch(const float *cube, const float *calib, int64_t npix, int C, OutT *out,
+template <typename OutT, typename InT>
+static int chansum_launch(const InT *cube, const float *calib, int64_t npix, int C, float scale, OutT *out,
                           unsigned long long *maxkey, cudaStream_t st) {
     int64_t done = 0;
     const bool aligned = (((uintptr_t)cube) & 15u) == 0 && (calib == nullptr || (((uintptr_t)calib) & 15u) == 0);
     if (aligned) {
-        const int per_px = (calib ? 2 : 1) * C * 4;   // bytes per pixel per stage
+        const int per_px = (calib ? 2 : 1) * C * (int)sizeof(InT);   // bytes per pixel per stage
         int cpx = 0;
         for (int cand = calib ? 64 : 128; cand >= 32; cand -= 32) {   // calib: two threads per pixel
             if ((int64_t)cand * per_px * 2 <= CS_INFLIGHT_TARGET) { cpx = cand; break; }
@@ -232,22 +242,28 @@ static int chansum_launch(const float *cube, const float *calib, int64_t npix, i
             int64_t grid = sm_count();
             if (grid > nchunks) grid = nchunks;
             const unsigned threads = groups * CS_GROUP_THREADS + 32;
-            if (calib) {
-                static bool attr_c[2] = {false, false};
-                auto kern = chansum_bulk_kernel<OutT, true>;
-                if (!attr_c[sizeof(OutT) == 8]) {
-                    HIPR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM_BUDGET));
-                    attr_c[sizeof(OutT) == 8] = true;
+            // (one static flag per template instantiation of this function)
+            if constexpr (sizeof(InT) == 4) {
+                if (calib) {
+                    static bool attr_c = false;
+                    auto kern = chansum_bulk_kernel<OutT, true, float>;
+                    if (!attr_c) {
+                        HIPR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM_BUDGET));
+                        attr_c = true;
+                    }
+                    kern<<<(unsigned)grid, threads, smem, st>>>(cube, calib, nchunks, C, cpx, stages, groups, scale, out,
+                                                               maxkey);
                 }
-                kern<<<(unsigned)grid, threads, smem, st>>>(cube, calib, nchunks, C, cpx, stages, groups, out, maxkey);
-            } else {
-                static bool attr_n[2] = {false, false};
-                auto kern = chansum_bulk_kernel<OutT, false>;
-                if (!attr_n[sizeof(OutT) == 8]) {
+            }
+            if (!calib) {
+                static bool attr_n = false;
+                auto kern = chansum_bulk_kernel<OutT, false, InT>;
+                if (!attr_n) {
                     HIPR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM_BUDGET));
-                    attr_n[sizeof(OutT) == 8] = true;
+                    attr_n = true;
                 }
-                kern<<<(unsigned)grid, threads, smem, st>>>(cube, nullptr, nchunks, C, cpx, stages, groups, out, maxkey);
+                kern<<<(unsigned)grid, threads, smem, st>>>(cube, nullptr, nchunks, C, cpx, stages, groups, scale, out,
+                                                           maxkey);
             }
             int e = after_launch();
             if (e) return e;
@@ -259,7 +275,7 @@ static int chansum_launch(const float *cube, const float *calib, int64_t npix, i
         int64_t blocks = (rest + 7) / 8;  // 8 warps per block, one pixel per warp per trip
         const int64_t cap = (int64_t)sm_count() * 8;
         if (blocks > cap) blocks = cap;
-        chansum_warp_kernel<OutT><<<(unsigned)blocks, 256, 0, st>>>(cube, calib, done, npix, C, out, maxkey);
+        chansum_warp_kernel<OutT, InT><<<(unsigned)blocks, 256, 0, st>>>(cube, calib, done, npix, C, scale, out, maxkey);
         int e = after_launch();
         if (e) return e;
     }
@@ -267,8 +283,12 @@ static int chansum_launch(const float *cube, const float *calib, int64_t npix, i
 }
 
 // used by the host-buffer pipeline: one band of rows, max key accumulated (not reset)
-int chansum_band(const float *cube, int64_t npix, int C, double *out, unsigned long long *maxkey, cudaStream_t st) {
-    return chansum_launch<double>(cube, nullptr, npix, C, out, maxkey, st);
+int chansum_band(const void *cube, int sample_bytes, float scale, int64_t npix, int C, double *out,
+                 unsigned long long *maxkey, cudaStream_t st) {
+    if (sample_bytes == 4) return chansum_launch<double, float>((const float *)cube, nullptr, npix, C, 1.f, out, maxkey, st);
+    if (sample_bytes == 2)
+        return chansum_launch<double, uint16_t>((const uint16_t *)cube, nullptr, npix, C, scale, out, maxkey, st);
+    return chansum_launch<double, uint8_t>((const uint8_t *)cube, nullptr, npix, C, scale, out, maxkey, st);
 }
 
 }  // namespace hipr
@@ -287,8 +307,22 @@ extern "C" int hipr_chansum(const float *cube_dev, const float *calib_dev, int64
     }
     unsigned long long *mk = reinterpret_cast<unsigned long long *>(maxkey_dev);
     if (sum_dtype == HIPR_F32)
-        return chansum_launch<float>(cube_dev, calib_dev, npix, C, (float *)sum_dev, mk, st);
-    return chansum_launch<double>(cube_dev, calib_dev, npix, C, (double *)sum_dev, mk, st);
+        return chansum_launch<float, float>(cube_dev, calib_dev, npix, C, 1.f, (float *)sum_dev, mk, st);
+    return chansum_launch<double, float>(cube_dev, calib_dev, npix, C, 1.f, (double *)sum_dev, mk, st);
+}
+
+extern "C" int hipr_chansum_raw(const void *cube_dev, int sample_bytes, double scale, int64_t npix, int C,
+                                double *sum_dev, uint64_t *maxkey_dev, void *stream) {
+    if (!cube_dev || !sum_dev || npix <= 0 || C <= 0 || !(scale > 0.0)) return HIPR_E_ARG;
+    if (sample_bytes != 1 && sample_bytes != 2) return HIPR_E_DTYPE;
+    if (sample_bytes == 2 && (((uintptr_t)cube_dev) & 1u)) return HIPR_E_ALIGN;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (maxkey_dev) {
+        HIPR_CUDA(cudaMemsetAsync(maxkey_dev, 0x00, sizeof(uint64_t), st));
+        HIPR_CUDA(cudaMemsetAsync(maxkey_dev + 1, 0xff, sizeof(uint64_t), st));
+    }
+    return chansum_band(cube_dev, sample_bytes, (float)scale, npix, C, sum_dev,
+                        reinterpret_cast<unsigned long long *>(maxkey_dev), st);
 }
 
 extern "C" int hipr_normalize(void *sum_dev, int sum_dtype, int64_t npix, const uint64_t *maxkey_dev,

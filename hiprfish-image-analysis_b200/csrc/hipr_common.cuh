@@ -187,6 +187,33 @@ __device__ __forceinline__ double sum_channels(const float *__restrict__ p, int 
     return (a0 + a1) + (a2 + a3);
 }
 
+// Raw detector counts -> the float32 value python-bioformats' load_image(rescale=True) hands the
+// scripts: image.astype(np.float32) / float(scale), one correctly rounded float32 divide per sample.
+template <typename InT>
+__device__ __forceinline__ float raw_value(InT v, float scale) {
+    return __fdiv_rn((float)v, scale);
+}
+template <typename InT>
+__device__ __forceinline__ double sum_channels_raw(const InT *__restrict__ p, int C, float scale) {
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int c = 0;
+    for (; c + 8 <= C; c += 8) {
+        InT v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = p[c + u];
+        a0 += (double)raw_value(v[0], scale);
+        a1 += (double)raw_value(v[1], scale);
+        a2 += (double)raw_value(v[2], scale);
+        a3 += (double)raw_value(v[3], scale);
+        a0 += (double)raw_value(v[4], scale);
+        a1 += (double)raw_value(v[5], scale);
+        a2 += (double)raw_value(v[6], scale);
+        a3 += (double)raw_value(v[7], scale);
+    }
+    for (; c < C; ++c) a0 += (double)raw_value(p[c], scale);
+    return (a0 + a1) + (a2 + a3);
+}
+
 // sum_c p[c] / q[c]: the flat-field divide of syn/..._measurement.py:104 followed by the channel sum
 // of :105.  numpy divides in float64; a float64 divide per channel (MUFU.RCP64H + ~10 dependent
 // DFMA) made the kernel latency-bound at a third of the HBM rate, so the quotient is formed as

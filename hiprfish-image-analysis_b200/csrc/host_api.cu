@@ -10,7 +10,8 @@ namespace hipr {
 
 std::atomic<int64_t> g_launches{0};
 
-int chansum_band(const float *cube, int64_t npix, int C, double *out, unsigned long long *maxkey, cudaStream_t st);
+int chansum_band(const void *cube, int sample_bytes, float scale, int64_t npix, int C, double *out,
+                 unsigned long long *maxkey, cudaStream_t st);
 
 constexpr int NBUF = 3;
 struct Workspace {
@@ -130,14 +131,17 @@ extern "C" int hipr_host_release_workspace(void) {
     return HIPR_OK;
 }
 
-extern "C" int hipr_neighbor2d_host(const float *cube_host, int H, int W, int C, int patch_size, int n_dirs,
-                                    const int32_t *table_host, int flavour, float *score_host, float *sum_host) {
+// cube_host: (H, W, C) samples of `sample_bytes` (4 = float32; 2 / 1 = raw uint16 / uint8 counts, value =
+// float32(count) / float32(scale))
+static int neighbor2d_host_impl(const void *cube_host, int sample_bytes, float scale, int H, int W, int C,
+                                int patch_size, int n_dirs, const int32_t *table_host, int flavour, float *score_host,
+                                float *sum_host) {
     if (!cube_host || !score_host || H < 1 || W < 1 || C < 1) return HIPR_E_ARG;
     Workspace &w = g_ws;
     std::lock_guard<std::mutex> lock(w.mu);
     int e = ws_init(w);
     if (e) return e;
-    const int64_t row_bytes = (int64_t)W * C * 4;
+    const int64_t row_bytes = (int64_t)W * C * sample_bytes;
     const int rows = band_rows(row_bytes, H);
     if ((e = ws_bands(w, (size_t)rows * row_bytes))) return e;
     const size_t img_bytes = (size_t)H * W * 4;
@@ -156,11 +160,12 @@ extern "C" int hipr_neighbor2d_host(const float *cube_host, int H, int W, int C,
         const int nr = (H - r0 < rows) ? H - r0 : rows;
         const int slot = b % NBUF;
         if (b >= NBUF) HIPR_CUDA(cudaStreamWaitEvent(w.copy, w.freed[slot], 0));
-        HIPR_CUDA(cudaMemcpyAsync(w.band[slot], cube_host + (int64_t)r0 * W * C, (size_t)nr * row_bytes,
+        HIPR_CUDA(cudaMemcpyAsync(w.band[slot], (const char *)cube_host + (int64_t)r0 * row_bytes, (size_t)nr * row_bytes,
                                   cudaMemcpyHostToDevice, w.copy));
         HIPR_CUDA(cudaEventRecord(w.copied[slot], w.copy));
         HIPR_CUDA(cudaStreamWaitEvent(w.comp, w.copied[slot], 0));
-        if ((e = chansum_band((const float *)w.band[slot], (int64_t)nr * W, C, sum_dev + (int64_t)r0 * W, key, w.comp)))
+        if ((e = chansum_band(w.band[slot], sample_bytes, scale, (int64_t)nr * W, C, sum_dev + (int64_t)r0 * W, key,
+                              w.comp)))
             return e;
         HIPR_CUDA(cudaEventRecord(w.freed[slot], w.comp));
     }
@@ -185,6 +190,21 @@ extern "C" int hipr_neighbor2d_host(const float *cube_host, int H, int W, int C,
     HIPR_CUDA(cudaStreamSynchronize(w.comp));
     HIPR_CUDA(cudaEventElapsedTime(&w.last_ms, w.t0, w.t1));
     return HIPR_OK;
+}
+
+extern "C" int hipr_neighbor2d_host(const float *cube_host, int H, int W, int C, int patch_size, int n_dirs,
+                                    const int32_t *table_host, int flavour, float *score_host, float *sum_host) {
+    return neighbor2d_host_impl(cube_host, 4, 1.f, H, W, C, patch_size, n_dirs, table_host, flavour, score_host, sum_host);
+}
+
+extern "C" int hipr_neighbor2d_host_raw(const void *cube_host, int sample_bytes, double scale, int H, int W, int C,
+                                        int patch_size, int n_dirs, const int32_t *table_host, int flavour,
+                                        float *score_host, float *sum_host) {
+    if (sample_bytes != 1 && sample_bytes != 2) return HIPR_E_DTYPE;
+    if (!(scale > 0.0)) return HIPR_E_ARG;
+    if (sample_bytes == 2 && (((uintptr_t)cube_host) & 1u)) return HIPR_E_ALIGN;
+    return neighbor2d_host_impl(cube_host, sample_bytes, (float)scale, H, W, C, patch_size, n_dirs, table_host, flavour,
+                                score_host, sum_host);
 }
 
 extern "C" double hipr_host_last_elapsed_ms(void) { return (double)g_ws.last_ms; }

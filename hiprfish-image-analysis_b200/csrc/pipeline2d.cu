@@ -13,7 +13,8 @@
 
 namespace hipr {
 
-int chansum_band(const float *cube, int64_t npix, int C, double *out, unsigned long long *maxkey, cudaStream_t st);
+int chansum_band(const void *cube, int sample_bytes, float scale, int64_t npix, int C, double *out,
+                 unsigned long long *maxkey, cudaStream_t st);
 int lne2d_q_rows(const void *image_dev, int Hs, int Ws, int64_t ld, int padded, int dtype, const int32_t *table_host,
                  int flavour, const uint64_t *range_dev, float *out_dev, int y_begin, int y_end, cudaStream_t st);
 
@@ -66,7 +67,7 @@ extern "C" int hipr_neighbor2d(const float *cube_dev, int H, int W, int C, int p
     const int nb = (H + band_rows - 1) / band_rows;
     int e;
     if (nb == 1) {
-        if ((e = chansum_band(cube_dev, (int64_t)H * W, C, sum_dev, rg, st))) return e;
+        if ((e = chansum_band(cube_dev, 4, 1.f, (int64_t)H * W, C, sum_dev, rg, st))) return e;
         return lne2d_q_rows(sum_dev, H, W, W, 0, HIPR_F64, table_host, flavour, local ? nullptr : range_dev, score_dev, 0,
                             H, st);
     }
@@ -77,7 +78,7 @@ extern "C" int hipr_neighbor2d(const float *cube_dev, int H, int W, int C, int p
     HIPR_CUDA(cudaStreamWaitEvent(sd->s, sd->start, 0));
     for (int b = 0; b < nb; ++b) {
         const int r0 = b * band_rows, r1 = (r0 + band_rows < H) ? r0 + band_rows : H;
-        if ((e = chansum_band(cube_dev + (int64_t)r0 * W * C, (int64_t)(r1 - r0) * W, C, sum_dev + (int64_t)r0 * W, rg, st)))
+        if ((e = chansum_band(cube_dev + (int64_t)r0 * W * C, 4, 1.f, (int64_t)(r1 - r0) * W, C, sum_dev + (int64_t)r0 * W, rg, st)))
             return e;
         HIPR_CUDA(cudaEventRecord(sd->k1[b], st));
         HIPR_CUDA(cudaStreamWaitEvent(sd->s, sd->k1[b], 0));

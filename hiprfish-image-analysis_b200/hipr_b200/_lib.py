@@ -16,6 +16,7 @@ _SIGNATURES = {
     "hipr_launch_count": (_i64, []),
     "hipr_sm_count": (_i, []),
     "hipr_chansum": (_i, [_vp, _vp, _i64, _i, _vp, _i, _vp, _vp]),
+    "hipr_chansum_raw": (_i, [_vp, _i, C.c_double, _i64, _i, _vp, _vp, _vp]),
     "hipr_register_stacks": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "hipr_image_range": (_i, [_vp, _i, _i64, _vp, _vp]),
     "hipr_normalize_cast": (_i, [_vp, _i64, _vp, _vp, _vp]),
@@ -37,6 +38,7 @@ _SIGNATURES = {
     "hipr_cell_spectra_reset": (_i, [_vp, _vp, _i64, _i, _vp]),
     "hipr_cell_spectra_finalize": (_i, [_vp, _vp, _i64, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "hipr_neighbor2d_host": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp]),
+    "hipr_neighbor2d_host_raw": (_i, [_vp, _i, C.c_double, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp]),
     "hipr_cell_spectra_host": (_i, [_vp, _vp, _i, _i64, _i64, _i, _i64, _vp, _vp, _vp, _vp, _vp]),
     "hipr_host_last_elapsed_ms": (C.c_double, []),
     "hipr_host_alloc": (_i, [C.POINTER(_vp), _i64]),

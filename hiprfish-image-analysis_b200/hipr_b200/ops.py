@@ -106,6 +106,24 @@ def channel_sum(cube, calibration=None, normalize=True, dtype=torch.float32, ret
     return (out, mk) if return_max else out
 
 
+def channel_sum_raw(cube, scale, return_max=False):
+    """cube (..., C) of raw detector counts (torch.uint8 / uint16 / int16 bit pattern of uint16) -> float64
+    channel sums of float32(count) / float32(scale), the values bioformats' rescale hands the scripts."""
+    if not isinstance(cube, torch.Tensor) or not cube.is_cuda:
+        raise ValueError("cube must be a CUDA tensor (there is no CPU path)")
+    if cube.dtype not in (torch.uint8, torch.uint16, torch.int16):
+        raise TypeError("raw cube must be uint8 or uint16, got %s" % cube.dtype)
+    cube = cube.contiguous()
+    Cn = cube.shape[-1]
+    npix = cube.numel() // Cn
+    out = torch.empty(cube.shape[:-1], dtype=torch.float64, device=cube.device)
+    mk = MaxKey(cube.device)
+    with torch.cuda.device(cube.device):
+        check(lib().hipr_chansum_raw(C.c_void_p(cube.data_ptr()), cube.element_size(), float(scale), npix, Cn,
+                                     C.c_void_p(out.data_ptr()), mk.ptr(), _stream()), "channel_sum_raw")
+    return (out, mk) if return_max else out
+
+
 def register_stacks(stacks, shifts=None, calibration=None, return_cube=True):
     """Registration paste + np.dstack + flat-field divide + channel sum in one pass (csrc/register.cu).
 
@@ -552,6 +570,23 @@ def neighbor2d_score_host(cube, flavour="F1", patch_size=11, phi_range=9, return
                                      _tab_ptr(tab), _flavour(flavour), score.ctypes.data_as(C.c_void_p),
                                      s.ctypes.data_as(C.c_void_p) if return_sum else None), "neighbor2d_host")
     return (score, s) if return_sum else score
+
+
+def neighbor2d_score_host_raw(cube, scale, flavour="F1", patch_size=11, phi_range=9, out=None):
+    """numpy (H, W, C) uint16 / uint8 raw counts -> numpy (H, W) float32 score map, the score of the cube
+    bioformats' rescale would produce (count / scale in float32), through hipr_neighbor2d_host_raw."""
+    cube = np.ascontiguousarray(cube)
+    if cube.dtype not in (np.uint8, np.uint16):
+        raise TypeError("raw cube must be uint8 or uint16, got %s" % cube.dtype)
+    if cube.ndim != 3:
+        raise ValueError("cube must be (H, W, C)")
+    H, W, Cn = cube.shape
+    tab = tables.line_table_2d(patch_size, phi_range)
+    score = out if out is not None else np.empty((H, W), dtype=np.float32)
+    check(lib().hipr_neighbor2d_host_raw(cube.ctypes.data_as(C.c_void_p), cube.itemsize, float(scale), H, W, Cn,
+                                         tab.shape[1], tab.shape[0], _tab_ptr(tab), _flavour(flavour),
+                                         score.ctypes.data_as(C.c_void_p), None), "neighbor2d_host_raw")
+    return score
 
 
 def cell_spectra_host(cube, labels):

@@ -77,6 +77,14 @@ int         hipr_sm_count(void);
 int hipr_chansum(const float *cube_dev, const float *calib_dev, int64_t npix, int C,
                  void *sum_dev, int sum_dtype, uint64_t *maxkey_dev, void *stream);
 
+/* Channel sum of RAW detector counts: cube_dev (npix, C) of uint16 (sample_bytes 2) or uint8 (1).  Each sample
+ * becomes the float32 value python-bioformats' load_image(rescale=True) hands the scripts at
+ * syn/..._measurement.py:81, image.astype(np.float32) / float(scale), one correctly rounded float32 divide,
+ * before the float64 channel sum: the same sums as hipr_chansum on the rescaled float32 cube, from half (a
+ * quarter) of the bytes.  sum_dev (npix) float64; maxkey_dev as hipr_chansum. */
+int hipr_chansum_raw(const void *cube_dev, int sample_bytes, double scale, int64_t npix, int C,
+                     double *sum_dev, uint64_t *maxkey_dev, void *stream);
+
 /* ---- registration paste + channel stack + flat field + channel sum, one pass --------------------
  * Replaces syn/..._measurement.py:86-105 (bio/..._analysis.py:330-348; eco/..._measurement.py:147-148
  * with zero shifts): the per-excitation images are pasted at their integer registration shifts
@@ -254,6 +262,11 @@ int hipr_cell_spectra_finalize(const double *sums_dev, const int32_t *counts_dev
 int hipr_neighbor2d_host(const float *cube_host, int H, int W, int C, int patch_size,
                          int n_dirs, const int32_t *table_host, int flavour,
                          float *score_host, float *sum_host);
+/* hipr_neighbor2d_host on raw uint16 / uint8 counts (see hipr_chansum_raw): half / a quarter of the PCIe
+ * traffic of the float32 cube, same score. */
+int hipr_neighbor2d_host_raw(const void *cube_host, int sample_bytes, double scale, int H, int W, int C,
+                             int patch_size, int n_dirs, const int32_t *table_host, int flavour,
+                             float *score_host, float *sum_host);
 int hipr_cell_spectra_host(const float *cube_host, const void *labels_host, int label_bytes,
                            int64_t npix, int64_t row_len, int C, int64_t capacity,
                            int64_t *n_cells,

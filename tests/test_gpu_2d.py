@@ -334,3 +334,42 @@ def test_channel_sum_calibration_bulk_path(torch_cuda, oracle):
     score = hipr_b200.neighbor2d_score(_cuda(torch_cuda, cube[small]), "F1", calibration=_cuda(torch_cuda, cal[small]))
     want_score = oracle.neighbor2d_score(cube[small], "F1", calibration=cal[small])
     np.testing.assert_allclose(score.cpu().numpy(), want_score, rtol=RTOL, atol=ATOL_FIXED)
+
+
+def _raw_cube(bits, shape=(96, 128, 95), fov=2):
+    """Raw detector counts with the structure of the synthetic FOV."""
+    from hipr_b200 import synth
+    cube = synth.make_fov(shape[0], shape[1], shape[2], fov_index=fov)[0].numpy()
+    top = (1 << bits) - 1
+    u = np.clip(np.round(cube / cube.max() * top * 0.9), 0, top)
+    return u.astype(np.uint16 if bits > 8 else np.uint8)
+
+
+@pytest.mark.parametrize("bits,scale", [(16, 65535.0), (12, 4095.0), (8, 255.0)])
+def test_channel_sum_raw_counts(torch_cuda, bits, scale):
+    """Raw uint16 / uint8 counts: every sample becomes float32(count) / float32(scale) (bioformats' rescale)
+    before the float64 channel sum -- the sums of the rescaled float32 cube, to the last bits."""
+    import hipr_b200
+    u = _raw_cube(bits, (37 * 4, 131, 95))                       # 19,388 px: bulk chunks + a ragged tail
+    f = u.astype(np.float32) / np.float32(scale)
+    want = f.astype(np.float64).sum(axis=2)
+    got, mk = hipr_b200.channel_sum_raw(torch_cuda.from_numpy(u).cuda(), scale, return_max=True)
+    np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-15, atol=0)
+    same, _ = hipr_b200.channel_sum(torch_cuda.from_numpy(f).cuda(), normalize=False, dtype=torch_cuda.float64, return_max=True)
+    assert torch_cuda.equal(got, same)                           # bit-identical to the float32 path
+    assert float(mk.value()) == got.max().item()
+
+
+def test_neighbor2d_host_raw_counts(torch_cuda, oracle):
+    """hipr_neighbor2d_host_raw on uint16 counts == the oracle on the rescaled float32 cube."""
+    import hipr_b200
+    u = _raw_cube(16)
+    f = u.astype(np.float32) / np.float32(65535.0)
+    want = oracle.neighbor2d_score(f, "F1")
+    got = hipr_b200.neighbor2d_score_host_raw(u, 65535.0, "F1")
+    np.testing.assert_allclose(got, want, rtol=RTOL, atol=ATOL_FIXED)
+    assert np.array_equal(got, hipr_b200.neighbor2d_score_host(f, "F1"))      # same sums -> same score, bit for bit
+    with pytest.raises(TypeError):
+        hipr_b200.neighbor2d_score_host_raw(f, 65535.0)
+    with pytest.raises(ValueError):
+        hipr_b200.neighbor2d_score_host_raw(u, 0.0)
