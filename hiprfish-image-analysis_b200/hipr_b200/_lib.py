@@ -24,6 +24,7 @@ _SIGNATURES = {
     "hipr_maxkey_decode": (_i, [_vp, _vp, _vp]),
     "hipr_range_decode": (_i, [_vp, _vp, _vp]),
     "hipr_range_encode": (_i, [_vp, _vp, _vp]),
+    "hipr_denoise_nl_means_2d": (_i, [_vp, _i, _i, _i, _i, _i, C.c_double, _vp, _vp]),
     "hipr_line_profile_2d": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "hipr_lne2d": (_i, [_vp, _i, _i, _i64, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp]),
     "hipr_lne2d_q": (_i, [_vp, _i, _i, _i64, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp]),

@@ -173,6 +173,22 @@ def neighbor2d_score_from_stacks(stacks, shifts=None, calibration=None, flavour=
     return score, cube, s64, mk
 
 
+def denoise_nl_means(image, patch_size=7, patch_distance=11, h=0.1):
+    """skimage.restoration.denoise_nl_means(image, h=h) for a 2-D image (fast mode, sigma 0), as
+    syn/...measurement.py:108 calls it on the normalised sum image.  (H, W) float32 / float64 CUDA tensor ->
+    same dtype.  csrc/nlm2d.cu; patch_size 7, patch_distance <= 15."""
+    image = _dev(image, "image")
+    if image.dim() != 2:
+        raise ValueError("image must be 2-D, got %d-D" % image.dim())
+    Hh, Ww = image.shape
+    out = torch.empty_like(image)
+    with torch.cuda.device(image.device):
+        check(lib().hipr_denoise_nl_means_2d(C.c_void_p(image.data_ptr()), Hh, Ww, _DT[image.dtype], int(patch_size),
+                                             int(patch_distance), float(h), C.c_void_p(out.data_ptr()), _stream()),
+              "denoise_nl_means")
+    return out
+
+
 def lne2d(image, flavour="F1", patch_size=11, phi_range=9, padded=False, maxkey=None):
     """Score map ("local neighbourhood enhancement") of a 2-D image.
 
@@ -217,8 +233,9 @@ def lne2d_fixed(image, flavour="F1", patch_size=11, phi_range=9, padded=False, r
     tab = tables.line_table_2d(patch_size, phi_range)
     if tab.shape[:2] != (9, 11):
         raise ValueError("the fixed-point stencil exists for patch_size=11, phi_range=9 only; use lne2d")
-    if range_keys is None:
-        range_keys = image_range(image)
+    if range_keys is None and _flavour(flavour) not in (1, 2):
+        range_keys = image_range(image)      # F3 scales its epsilon by the global range
+    # F1 / F2 with no keys: every 32x32 tile is quantised with its own min / max (finest resolution)
     Hs, Ws = image.shape
     H, W = (Hs - 10, Ws - 10) if padded else (Hs, Ws)
     if H < 1 or W < 1:
@@ -226,8 +243,8 @@ def lne2d_fixed(image, flavour="F1", patch_size=11, phi_range=9, padded=False, r
     out = torch.empty((H, W), dtype=torch.float32, device=image.device)
     with torch.cuda.device(image.device):
         check(lib().hipr_lne2d_q(C.c_void_p(image.data_ptr()), Hs, Ws, Ws, int(bool(padded)), _DT[image.dtype], 11, 9,
-                                 _tab_ptr(tab), _flavour(flavour), range_keys.ptr(), C.c_void_p(out.data_ptr()),
-                                 _stream()), "lne2d_fixed")
+                                 _tab_ptr(tab), _flavour(flavour), range_keys.ptr() if range_keys is not None else None,
+                                 C.c_void_p(out.data_ptr()), _stream()), "lne2d_fixed")
     return out
 
 
@@ -288,14 +305,24 @@ def neighbor2d_pipeline(cube, flavour="F1", patch_size=11, phi_range=9, bands=0)
 
 
 def neighbor2d_score(cube, flavour="F1", calibration=None, patch_size=11, phi_range=9, dtype=None,
-                     return_sum=False):
+                     return_sum=False, denoise_h=None):
     """cube (H, W, C) or (N, H, W, C) float32 -> score map(s) (H, W) / (N, H, W).
 
-    channel sum -> /max -> edge pad -> line profiles -> epilogue, FOV by FOV (each FOV has its
-    own max).  dtype=None (default): float64 channel sums feed the fixed-point stencil
+    channel sum -> /max -> [NL-means denoise] -> edge pad -> line profiles -> epilogue, FOV by FOV (each
+    FOV has its own max).  dtype=None (default): float64 channel sums feed the fixed-point stencil
     (lne2d_fixed; float32 score).  dtype=torch.float32 / float64: the sum image is stored in that
-    type and the floating-point stencil of that type runs, dividing by the max on load."""
+    type and the floating-point stencil of that type runs, dividing by the max on load.
+    denoise_h: None, or the `h` of skimage.restoration.denoise_nl_means applied to the normalised sum
+    image before the stencil (0.02 at syn/...measurement.py:108): the whole chain stays on the device."""
     cube = _dev(cube, "cube", (torch.float32,))
+    if denoise_h is not None and cube.dim() == 3:
+        s = channel_sum(cube, calibration, normalize=True, dtype=torch.float64)
+        den = denoise_nl_means(s, h=denoise_h)
+        # the denoised image is smooth: its 11-sample lines span ~1e-4 of a tile's range, below what the
+        # 31-bit fixed-point stencil resolves to 1e-5 (measured 5e-6), so the float64 stencil runs here
+        # (0.25 ms at 2048^2, next to ~9 ms of denoising)
+        score = lne2d(den if dtype in (None, torch.float64) else den.to(dtype), flavour, patch_size, phi_range)
+        return (score, den) if return_sum else score
     if cube.dim() == 4:
         # independent FOVs alternate between two streams: FOV i+1's channel sum (HBM-bound) runs
         # under FOV i's stencil (SM-bound); joined on the caller's stream before returning
@@ -307,7 +334,7 @@ def neighbor2d_score(cube, flavour="F1", calibration=None, patch_size=11, phi_ra
         for i, c in enumerate(cube):
             with torch.cuda.stream(side[i % len(side)]):
                 res.append(neighbor2d_score(c, flavour, None if calibration is None else calibration, patch_size,
-                                            phi_range, dtype, return_sum))
+                                            phi_range, dtype, return_sum, denoise_h))
         for st in side:
             cur.wait_stream(st)
         for r in res:

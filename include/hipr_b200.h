@@ -121,6 +121,17 @@ int hipr_maxkey_decode(const uint64_t *maxkey_dev, double *max_dev, void *stream
 int hipr_range_decode(const uint64_t *range_dev, double *maxmin_dev, void *stream);
 int hipr_range_encode(const double *maxmin_dev, uint64_t *range_dev, void *stream);
 
+/* ---- non-local-means denoise of the sum image --------------------------------------------------
+ * Replaces skimage.restoration.denoise_nl_means(image, h = h) as the 2-D callers use it (fast mode,
+ * patch_size 7, patch_distance 11, sigma 0): syn/..._measurement.py:108, bio/..._analysis.py:350, 592, 668,
+ * 725, 989.  image_dev, out_dev (H, W) of dtype; H, W > offset + patch_distance + 1 (a single reflection of
+ * the border, as np.pad(mode='reflect') on such images).  patch_size 7 (or 6, which skimage makes 7) only,
+ * patch_distance <= 15 (HIPR_E_UNSUPPORTED otherwise).  scikit-image is not pinned by the reference and is
+ * not available to the oracle: parity is against the restated algorithm (oracle/hipr_oracle.py).
+ */
+int hipr_denoise_nl_means_2d(const void *image_dev, int H, int W, int dtype, int patch_size,
+                             int patch_distance, double h, void *out_dev, void *stream);
+
 /* ---- 2-D literal stencil ------------------------------------------------------------------
  * Replaces line_profile_2d_v2(image_padded, patch_size, phi_range), eco/neighbor2d.pyx:8-64:
  *   out[i, j, t, li] = image_padded[i + table[t, li, 0], j + table[t, li, 1]]

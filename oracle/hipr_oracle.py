@@ -256,6 +256,109 @@ def register_stacks(image_stack, shift_vectors, calibration_image=None):
     return image_channel, np.sum(image_channel, axis=2)
 
 
+NLM_DISTANCE_CUTOFF = 5.0
+
+
+def denoise_nl_means_2d(image, patch_size=7, patch_distance=11, h=0.1, sigma=0.0):
+    """skimage.restoration.denoise_nl_means(image, h=h) for a 2-D grayscale image with the defaults the
+    scripts use (fast_mode=True, patch_size=7, patch_distance=11, sigma=0):
+    syn/hiprfish_imaging_multispecies_spectral_image_measurement.py:108 (h = 0.02),
+    bio/hiprfish_imaging_biofilm_analysis.py:350, 592, 668, 725, 989.
+
+    PARITY UNPINNED: scikit-image is a third-party dependency that the reference neither vendors nor pins
+    (era 0.14-0.15) and it is not installed here.  This restates the published algorithm of
+    skimage/restoration/_nl_means_denoising.pyx::_fast_nl_means_denoising_2d (Darbon et al. 2008, integral
+    images of squared differences, one per patch shift), loop for loop:
+      * reflect padding by offset + d + 1, offset = patch_size // 2;
+      * for every shift (t_row in [-d, d], t_col in [0, d]): integral image of (padded - shifted)^2 - 2 sigma^2;
+        patch distance from its four corners at +-offset (a 2*offset square, NOT patch_size: a quirk of
+        the implementation), clipped at 0 and divided by h^2 * patch_size^2;
+      * weight = alpha * exp(-distance) unless distance > 5, alpha = 0.5 on the t_col = 0, t_row != 0
+        column (visited from both sides); accumulated symmetrically into both pixels of the pair (so the
+        zero shift counts twice);
+      * result / weights, cropped.
+    Vectorised over pixels (numpy), one shift at a time.  Test infrastructure only."""
+    image = np.asarray(image, dtype=np.float64)
+    if image.ndim != 2:
+        raise ValueError("2-D grayscale images only")
+    s = int(patch_size)
+    if s % 2 == 0:
+        s += 1
+    d = int(patch_distance)
+    offset = s // 2
+    pad_size = offset + d + 1
+    padded = np.pad(image, pad_size, mode="reflect")
+    n_row, n_col = padded.shape
+    result = np.zeros_like(padded)
+    weights = np.zeros_like(padded)
+    h2s2 = h * h * s * s            # n_channels = 1
+    var = 2.0 * sigma * sigma
+    for t_row in range(-d, d + 1):
+        row_start = max(offset, offset - t_row)
+        row_end = min(n_row - offset, n_row - offset - t_row)
+        for t_col in range(0, d + 1):
+            alpha = 0.5 if (t_col == 0 and t_row != 0) else 1.0
+            # _integral_image_2d
+            integral = np.zeros_like(padded)
+            ra, rb = max(1, -t_row), min(n_row, n_row - t_row)
+            ca, cb = 1, n_col - t_col
+            diff = (padded[ra:rb, ca:cb] - padded[ra + t_row:rb + t_row, ca + t_col:cb + t_col]) ** 2 - var
+            integral[ra:rb, ca:cb] = np.cumsum(np.cumsum(diff, axis=0), axis=1)
+            # inner loops on pixel coordinates
+            col_start, col_end = offset, n_col - offset - t_col
+            R = slice(row_start, row_end)
+            Cs = slice(col_start, col_end)
+            dist = (integral[row_start + offset:row_end + offset, col_start + offset:col_end + offset]
+                    + integral[row_start - offset:row_end - offset, col_start - offset:col_end - offset]
+                    - integral[row_start - offset:row_end - offset, col_start + offset:col_end + offset]
+                    - integral[row_start + offset:row_end + offset, col_start - offset:col_end - offset])
+            dist = np.maximum(dist, 0.0) / h2s2
+            w = np.where(dist > NLM_DISTANCE_CUTOFF, 0.0, alpha * np.exp(-dist))
+            Rs = slice(row_start + t_row, row_end + t_row)
+            Css = slice(col_start + t_col, col_end + t_col)
+            weights[R, Cs] += w
+            weights[Rs, Css] += w
+            result[R, Cs] += w * padded[Rs, Css]
+            result[Rs, Css] += w * padded[R, Cs]
+    out = result[pad_size:-pad_size, pad_size:-pad_size] / weights[pad_size:-pad_size, pad_size:-pad_size]
+    return out
+
+
+def denoise_nl_means_2d_direct(image, patch_size=7, patch_distance=11, h=0.1):
+    """The same estimator written pixel by pixel (no integral images, no symmetric accumulation): for every
+    pixel p and every shift t in [-d, d]^2, weight = exp(-max(sum over the 2*offset window of
+    (v[u] - v[u + t])^2, 0) / (h^2 s^2)) if that distance is <= 5, the zero shift counted twice.  Used to
+    check the restatement above against an independent formulation (tests/test_oracle.py); O(N d^2 s^2)."""
+    image = np.asarray(image, dtype=np.float64)
+    s = int(patch_size) | 1
+    d = int(patch_distance)
+    offset = s // 2
+    pad = offset + d + 1
+    v = np.pad(image, pad, mode="reflect")
+    H, W = image.shape
+    h2s2 = h * h * s * s
+    acc_w = np.zeros((H, W))
+    acc_v = np.zeros((H, W))
+    lo, hi = -offset + 1, offset        # window rows / cols p + lo .. p + hi
+    for tr in range(-d, d + 1):
+        for tc in range(-d, d + 1):
+            a = v[pad + lo: pad + H + hi, pad + lo: pad + W + hi]
+            b = v[pad + lo + tr: pad + H + hi + tr, pad + lo + tc: pad + W + hi + tc]
+            D = (a - b) ** 2                                  # (H + 2*offset - 1, W + 2*offset - 1)
+            box = np.zeros((H, W))
+            n = hi - lo + 1
+            for i in range(n):
+                for j in range(n):
+                    box += D[i:i + H, j:j + W]
+            dist = np.maximum(box, 0.0) / h2s2
+            w = np.where(dist > NLM_DISTANCE_CUTOFF, 0.0, np.exp(-dist))
+            if tr == 0 and tc == 0:
+                w = 2.0 * w
+            acc_w += w
+            acc_v += w * v[pad + tr: pad + tr + H, pad + tc: pad + tc + W]
+    return acc_v / acc_w
+
+
 def _mean_quartiles(rnc, axis):
     m = np.average(rnc, axis=axis)
     with np.errstate(invalid="ignore"):

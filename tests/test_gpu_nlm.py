@@ -1,0 +1,63 @@
+"""GPU parity of the non-local-means kernel (csrc/nlm2d.cu) against the oracle's restatement of
+skimage.restoration.denoise_nl_means (fast mode).  PARITY UNPINNED at the skimage boundary: scikit-image is
+not installed here and the reference does not pin it (oracle/hipr_oracle.py::denoise_nl_means_2d)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+RTOL_NLM = 1e-12     # float64 throughout; the oracle's integral images carry ~1e-13 of their own
+
+
+def _image(shape, seed, noise=0.03):
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:shape[0], 0:shape[1]]
+    img = (np.sin(yy / 5.0) ** 2 + np.cos(xx / 7.0) ** 2) / 2 + noise * rng.random(shape)
+    return img / img.max()
+
+
+@pytest.mark.parametrize("shape,h,d", [((100, 90), 0.02, 11), ((64, 64), 0.1, 11), ((33, 47), 0.03, 11),
+                                        ((70, 40), 0.02, 5), ((16, 16), 0.05, 11), ((129, 65), 0.02, 15)])
+def test_nlm_matches_oracle(torch_cuda, oracle, shape, h, d):
+    import hipr_b200
+    if min(shape) <= 3 + d + 1:
+        pytest.skip("image smaller than the reflection pad")
+    img = _image(shape, shape[0] + d)
+    want = oracle.denoise_nl_means_2d(img, patch_distance=d, h=h)
+    got = hipr_b200.denoise_nl_means(torch_cuda.from_numpy(img).cuda(), patch_distance=d, h=h)
+    assert got.dtype == torch_cuda.float64
+    np.testing.assert_allclose(got.cpu().numpy(), want, rtol=RTOL_NLM, atol=0)
+    got32 = hipr_b200.denoise_nl_means(torch_cuda.from_numpy(img.astype(np.float32)).cuda(), patch_distance=d, h=h)
+    want32 = oracle.denoise_nl_means_2d(img.astype(np.float32), patch_distance=d, h=h)
+    np.testing.assert_allclose(got32.cpu().numpy(), want32, rtol=2e-7 + RTOL_NLM, atol=0)
+
+
+def test_chain_sum_denoise_score(torch_cuda, oracle):
+    """The whole 2-D chain of syn/..._measurement.py:105-124: channel sum -> /max -> NL-means (h = 0.02) ->
+    edge pad -> line profiles -> F1 epilogue, device-resident, against the oracle chain."""
+    import hipr_b200
+    from hipr_b200 import synth
+    cube = synth.make_fov(96, 128, 95, fov_index=5)[0]
+    s = cube.numpy().astype(np.float64).sum(axis=2)
+    s = s / s.max()
+    den = oracle.denoise_nl_means_2d(s, h=0.02)
+    want = oracle.lne2d(den, "F1")
+    got = hipr_b200.neighbor2d_score(cube.cuda(), "F1", denoise_h=0.02)
+    np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-6, atol=1e-9)
+
+
+def test_nlm_argument_errors(torch_cuda):
+    import hipr_b200
+    img = torch_cuda.rand((40, 40), device="cuda", dtype=torch_cuda.float64)
+    with pytest.raises(ValueError):
+        hipr_b200.denoise_nl_means(img, patch_size=9)            # only the scripts' patch size
+    with pytest.raises(ValueError):
+        hipr_b200.denoise_nl_means(img, patch_distance=16)
+    with pytest.raises(ValueError):
+        hipr_b200.denoise_nl_means(img[:15], h=0.02)             # smaller than the reflection pad
+    with pytest.raises(ValueError):
+        hipr_b200.denoise_nl_means(img, h=0.0)
+    with pytest.raises(ValueError):
+        hipr_b200.denoise_nl_means(img.cpu())
+    flat = torch_cuda.full((32, 32), 0.25, device="cuda", dtype=torch_cuda.float64)
+    assert torch_cuda.allclose(hipr_b200.denoise_nl_means(flat, h=0.02), flat, rtol=1e-13, atol=0)

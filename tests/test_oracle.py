@@ -142,3 +142,32 @@ def test_register_stacks_is_a_shifted_paste(oracle):
     cal = 0.5 + rng.random((H, W, 9))
     cube2, s2 = oracle.register_stacks(stacks, shifts, cal)
     assert np.array_equal(cube2, want / cal) and np.array_equal(s2, (want / cal).sum(axis=2))
+
+
+def _nlm_image(shape, seed):
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:shape[0], 0:shape[1]]
+    img = (np.sin(yy / 5.0) ** 2 + np.cos(xx / 7.0) ** 2) / 2 + 0.03 * rng.random(shape)
+    return img / img.max()
+
+
+@pytest.mark.parametrize("h,d", [(0.02, 11), (0.1, 11), (0.03, 4)])
+def test_nlm_restatement_equals_direct_formulation(oracle, h, d):
+    """PARITY UNPINNED (scikit-image absent): the loop-for-loop restatement of skimage's fast NL-means
+    (integral images, symmetric accumulation) equals the estimator written pixel by pixel."""
+    img = _nlm_image((31, 29), 1)
+    a = oracle.denoise_nl_means_2d(img, patch_distance=d, h=h)
+    b = oracle.denoise_nl_means_2d_direct(img, patch_distance=d, h=h)
+    np.testing.assert_allclose(a, b, rtol=1e-12)
+
+
+def test_nlm_properties(oracle):
+    img = _nlm_image((40, 36), 2)
+    out = oracle.denoise_nl_means_2d(img, h=0.02)
+    assert out.shape == img.shape and out.min() >= img.min() - 1e-12 and out.max() <= img.max() + 1e-12   # convex weights
+    flat = np.full((24, 24), 0.3)
+    np.testing.assert_allclose(oracle.denoise_nl_means_2d(flat, h=0.02), flat, rtol=1e-13)
+    # a tiny h keeps only the zero shift (every other patch is further than the cutoff): identity
+    np.testing.assert_allclose(oracle.denoise_nl_means_2d(img, h=1e-4), img, rtol=1e-14)
+    # even patch sizes are made odd, as skimage does
+    assert np.array_equal(oracle.denoise_nl_means_2d(img, patch_size=6, h=0.05), oracle.denoise_nl_means_2d(img, patch_size=7, h=0.05))
