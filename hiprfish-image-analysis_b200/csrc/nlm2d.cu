@@ -10,11 +10,12 @@
 //     w(p, t) = exp(-dist) if dist <= 5 else 0,  twice that for t = 0,
 //     dist    = max(sum_{u in W(p)} (v[u] - v[u + t])^2, 0) / (h^2 s^2),
 //     W(p)    = rows / cols p - offset + 1 .. p + offset   (a 2*offset square: the implementation's quirk),
-// on the reflect-padded image.  This kernel evaluates that directly: a CTA owns a 32 x 32 output tile,
-// holds the (32 + 2d + 2 offset - 1)^2 neighbourhood in shared memory and walks the (2d + 1)^2 shifts.
-// Per shift, phase 1 forms the horizontal 6-sums of squared differences (lanes along rows, eight
-// columns per thread so neighbouring sums share their terms: 26 LDS for 8 sums), phase 2 adds six of
-// them vertically for four pixels per thread, applies exp and accumulates weight and weighted value.
+// on the reflect-padded image.  This kernel evaluates that directly: a CTA owns a 56-row x 32-column
+// output tile, holds its (56 + 2d + 5) x (32 + 2d + 5) neighbourhood in shared memory and walks the
+// (2d + 1)^2 shifts.  Per shift, phase 1 forms the horizontal 6-sums of squared differences (lanes along
+// rows -- 61 rows fill two 32-lane blocks -- eight columns per thread so neighbouring sums share their
+// terms: 26 LDS for 8 sums), phase 2 adds six of them vertically for seven pixels per thread (sliding),
+// applies exp and accumulates weight and weighted value.
 // The sum buffers are double-buffered: one __syncthreads per shift.  Compute-bound (~150 instructions
 // per thread per shift, 529 shifts): this is 500x the arithmetic of the stencil.
 // Everything up to the distance is float64 (the B200's FP64 pipe runs at half the FP32 rate): the hard
@@ -24,11 +25,13 @@
 
 namespace hipr {
 
-constexpr int NL_T = 32;              // output tile side
+constexpr int NL_TC = 32;             // output tile: 32 columns (one per lane) ...
+constexpr int NL_TR = 56;             // ... x 56 rows (7 per warp)
+constexpr int NL_PPT = NL_TR / 8;     // pixels per thread
 constexpr int NL_OFF = 3;             // patch_size 7
 constexpr int NL_N = 2 * NL_OFF;      // window side (6)
-constexpr int NL_HR = NL_T + NL_N - 1;  // rows of horizontal sums per tile (37)
-constexpr int NL_HS = NL_T + 1;       // row stride of the sum buffers (odd: lanes along rows hit 32 banks)
+constexpr int NL_HR = NL_TR + NL_N - 1;  // rows of horizontal sums per tile (61: two blocks of 32 lanes)
+constexpr int NL_HS = NL_TC + 1;      // row stride of the sum buffers (odd: lanes along rows hit 32 banks)
 constexpr int NL_MAX_D = 15;
 
 __device__ __forceinline__ int reflect_index(int i, int n) {
@@ -38,92 +41,132 @@ __device__ __forceinline__ int reflect_index(int i, int n) {
     return min(max(i, 0), n - 1);   // beyond one reflection: only for tile cells no written pixel uses
 }
 
+// e^x for x in [-6, 0] to ~4e-11 relative: round(x log2 e) by the 1.5 * 2^52 trick, Cody-Waite reduction
+// to |r| <= ln2 / 2, then e^r = 1 + r (1 + r (1/2 + r (1/6 + r q(r)))) with the tail q = 1/4! + r/5! + ...
+// + r^8/12! evaluated in float32 (it enters multiplied by r^4 <= 1.5e-2, so its 6e-8 becomes < 4e-11), and
+// the exponent added to the high word.  8 FP64 + 8 FP32 operations, branch-free, so the seven pixels of a
+// thread interleave; CUDA's exp() cost 65 instructions behind a branch here, and the FP64 pipe is what
+// bounds this kernel.  (Weights accurate to 1e-10 keep the denoised image, and the line normalisation
+// that amplifies it ~1e4 times, far inside the 1e-5 gate.)
+__device__ __forceinline__ double exp_small_neg(double x) {
+    const double magic = 6755399441055744.0;
+    const double t = fma(x, 1.4426950408889634, magic);
+    const int n = __double2loint(t);
+    const double nf = t - magic;
+    double r = fma(nf, -6.93147180369123816490e-01, x);
+    r = fma(nf, -1.90821492927058770002e-10, r);
+    const float rf = (float)r;
+    float q = 2.08767569878680989792e-09f;            // 1 / 12!
+    q = fmaf(q, rf, 2.50521083854417187751e-08f);     // 1 / 11!
+    q = fmaf(q, rf, 2.75573192239858906526e-07f);
+    q = fmaf(q, rf, 2.75573192239858906526e-06f);
+    q = fmaf(q, rf, 2.48015873015873015873e-05f);
+    q = fmaf(q, rf, 1.98412698412698412698e-04f);
+    q = fmaf(q, rf, 1.38888888888888888889e-03f);
+    q = fmaf(q, rf, 8.33333333333333333333e-03f);
+    q = fmaf(q, rf, 4.16666666666666666667e-02f);     // 1 / 4!
+    double p = fma((double)q, r, 1.66666666666666666667e-01);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+}
+
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 nlm2d_kernel(const T *__restrict__ img, int H, int W, int d, double inv_h2s2, T *__restrict__ out) {
     extern __shared__ __align__(16) double nl_smem[];
-    const int TS = NL_T + 2 * d + NL_N - 1;      // tile side (59 for d = 11)
-    const int TP = TS | 1;                       // odd row stride
-    double *tile = nl_smem;                      // [TS][TP]
-    double *hb = nl_smem + TS * TP;              // [2][NL_HR][NL_HS]
+    const int TSR = NL_TR + 2 * d + NL_N - 1;    // tile rows (83 for d = 11)
+    const int TSC = NL_TC + 2 * d + NL_N - 1;    // tile columns (59)
+    const int TP = TSC | 1;                      // odd row stride
+    double *tile = nl_smem;                      // [TSR][TP]
+    double *hb = nl_smem + TSR * TP;             // [2][NL_HR][NL_HS]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int r0 = blockIdx.y * NL_T, c0 = blockIdx.x * NL_T;
+    const int r0 = blockIdx.y * NL_TR, c0 = blockIdx.x * NL_TC;
     // tile origin: first window row (r0 - offset + 1) minus d
     const int tr0 = r0 - NL_OFF + 1 - d, tc0 = c0 - NL_OFF + 1 - d;
-    for (int i = tid; i < TS * TS; i += 256) {
-        const int ly = i / TS, lx = i - ly * TS;
+    for (int i = tid; i < TSR * TSC; i += 256) {
+        const int ly = i / TSC, lx = i - ly * TSC;
         const int gy = reflect_index(tr0 + ly, H), gx = reflect_index(tc0 + lx, W);
         tile[ly * TP + lx] = (double)img[(int64_t)gy * W + gx];
     }
     __syncthreads();
-    // phase-1 work item: rows lane + 32 * (warp >> 2), eight columns starting at 8 * (warp & 3)
+    // phase-1 work item: row lane + 32 * (warp >> 2), eight columns starting at 8 * (warp & 3)
     const int h_row = lane + 32 * (warp >> 2);
     const int h_col = 8 * (warp & 3);
     const bool h_on = h_row < NL_HR;
-    // phase-2 pixels: column lane, rows 4 * warp .. + 3
-    const int p_row = 4 * warp;
-    double acc_w[4] = {0.0, 0.0, 0.0, 0.0}, acc_v[4] = {0.0, 0.0, 0.0, 0.0};
-    int buf = 0;
-    auto phase1 = [&](int tr, int tc, double *hbuf) {
+    // phase-2 pixels: column lane, rows NL_PPT * warp .. + NL_PPT - 1
+    const int p_row = NL_PPT * warp;
+    double acc_w[NL_PPT], acc_v[NL_PPT];
+#pragma unroll
+    for (int q = 0; q < NL_PPT; ++q) acc_w[q] = acc_v[q] = 0.0;
+    const double *a_base = tile + (h_row + d) * TP + h_col + d;
+    double *h_st = hb + h_row * NL_HS + h_col;
+    auto phase1 = [&](int tr, int tc, int which) {
         if (!h_on) return;
-        const double *a = tile + (h_row + d) * TP + h_col + d;
-        const double *b = a + tr * TP + tc;
+        const double *b = a_base + tr * TP + tc;
         double D[8 + NL_N - 1];
 #pragma unroll
         for (int k = 0; k < 8 + NL_N - 1; ++k) {
-            const double df = a[k] - b[k];
+            const double df = a_base[k] - b[k];
             D[k] = df * df;
         }
+        double *dst = h_st + which * (NL_HR * NL_HS);
         double s = D[0];
 #pragma unroll
         for (int k = 1; k < NL_N; ++k) s += D[k];
-        hbuf[h_row * NL_HS + h_col] = s;
+        dst[0] = s;
 #pragma unroll
         for (int m = 1; m < 8; ++m) {
             s += D[m + NL_N - 1] - D[m - 1];          // sliding window (float64: ~1e-16 of the largest term)
-            hbuf[h_row * NL_HS + h_col + m] = s;
+            dst[m] = s;
         }
     };
-    const int nshift = (2 * d + 1) * (2 * d + 1);
-    phase1(-d, -d, hb);
+    int buf = 0;
+    phase1(-d, -d, 0);
     __syncthreads();
-    for (int sidx = 0; sidx < nshift; ++sidx) {
-        const int tr = sidx / (2 * d + 1) - d, tc = sidx % (2 * d + 1) - d;
-        // phase 1 of the next shift fills the other buffer while this shift's sums are consumed
-        if (sidx + 1 < nshift) {
-            const int ntr = (sidx + 1) / (2 * d + 1) - d, ntc = (sidx + 1) % (2 * d + 1) - d;
-            phase1(ntr, ntc, hb + (buf ^ 1) * NL_HR * NL_HS);
-        }
-        const double *hcur = hb + buf * NL_HR * NL_HS + p_row * NL_HS + lane;
-        double hs[4 + NL_N - 1];
+    const double *h_ld = hb + p_row * NL_HS + lane;
+    // the shifted pixel p + t: tile coordinates (p - tile origin) = (row + offset - 1 + d + t_row, ...)
+    const double *v_base = tile + (p_row + NL_OFF - 1 + d) * TP + lane + NL_OFF - 1 + d;
+    for (int tr = -d; tr <= d; ++tr) {
+        for (int tc = -d; tc <= d; ++tc) {
+            // phase 1 of the next shift fills the other buffer while this shift's sums are consumed
+            int ntr = tr, ntc = tc + 1;
+            if (ntc > d) { ntc = -d; ++ntr; }
+            if (ntr <= d) phase1(ntr, ntc, buf ^ 1);
+            const double *hcur = h_ld + buf * (NL_HR * NL_HS);
+            double hs[NL_PPT + NL_N - 1];
 #pragma unroll
-        for (int k = 0; k < 4 + NL_N - 1; ++k) hs[k] = hcur[k * NL_HS];
-        const double self = (tr == 0 && tc == 0) ? 2.0 : 1.0;
-        // the shifted pixel p + t: tile coordinates (p - tile origin) = (row + offset - 1 + d, ...)
-        const double *vs = tile + (p_row + NL_OFF - 1 + d + tr) * TP + lane + NL_OFF - 1 + d + tc;
-        double box = hs[0];
+            for (int k = 0; k < NL_PPT + NL_N - 1; ++k) hs[k] = hcur[k * NL_HS];
+            const double *vs = v_base + tr * TP + tc;
+            double box = hs[0];
 #pragma unroll
-        for (int k = 1; k < NL_N; ++k) box += hs[k];
+            for (int k = 1; k < NL_N; ++k) box += hs[k];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            if (q > 0) box += hs[q + NL_N - 1] - hs[q - 1];
-            const double dist = fmax(box, 0.0) * inv_h2s2;
-            if (dist <= 5.0) {
-                // float64 exp: the denoised image feeds the line normalisation (centre - min) / (max - min), whose
-                // ranges on a denoised image are ~1e-3 of the values -- a float32 weight (1e-7) would surface as
-                // 1e-4 in the score
-                const double w = self * exp(-dist);
+            for (int q = 0; q < NL_PPT; ++q) {
+                if (q > 0) box += hs[q + NL_N - 1] - hs[q - 1];
+                // |box| for max(box, 0): the sliding sums can undershoot 0 by ~1e-18, which either way is dist = 0
+                const double dist = fabs(box) * inv_h2s2;
+                // dist <= 5.0 on the bit pattern (non-negative doubles order as integers): keeps the compare off
+                // the FP64 pipe
+                const int hi = __double2hiint(dist);
+                const bool inside = (hi < 0x40140000) || (hi == 0x40140000 && __double2loint(dist) == 0);
+                // beyond the cutoff exp_small_neg returns garbage (its exponent arithmetic wraps), discarded here
+                double w = exp_small_neg(-dist);
+                w = inside ? w : 0.0;
                 acc_w[q] += w;
                 acc_v[q] = fma(w, vs[q * TP], acc_v[q]);
             }
+            buf ^= 1;
+            __syncthreads();
         }
-        buf ^= 1;
-        __syncthreads();
     }
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < NL_PPT; ++q) {
         const int r = r0 + p_row + q, c = c0 + lane;
-        if (r < H && c < W) out[(int64_t)r * W + c] = (T)(acc_v[q] / acc_w[q]);
+        // the zero shift counts twice (skimage accumulates it into both ends of the pair, which coincide)
+        const double w = acc_w[q] + 1.0, v = acc_v[q] + v_base[q * TP];
+        if (r < H && c < W) out[(int64_t)r * W + c] = (T)(v / w);
     }
 }
 
@@ -140,16 +183,16 @@ extern "C" int hipr_denoise_nl_means_2d(const void *image_dev, int H, int W, int
     const int pad = NL_OFF + patch_distance + 1;
     if (H <= pad || W <= pad) return HIPR_E_PATCH;   // single reflection only (np.pad would wrap again)
     const int d = patch_distance;
-    const int TS = NL_T + 2 * d + NL_N - 1, TP = TS | 1;
-    const size_t smem = ((size_t)TS * TP + 2 * NL_HR * NL_HS) * sizeof(double);
+    const int TSR = NL_TR + 2 * d + NL_N - 1, TSC = NL_TC + 2 * d + NL_N - 1, TP = TSC | 1;
+    const size_t smem = ((size_t)TSR * TP + 2 * NL_HR * NL_HS) * sizeof(double);
     const double inv = 1.0 / (h * h * 49.0);
     static bool attr = false;
     if (!attr) {
-        HIPR_CUDA(cudaFuncSetAttribute(nlm2d_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        HIPR_CUDA(cudaFuncSetAttribute(nlm2d_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        HIPR_CUDA(cudaFuncSetAttribute(nlm2d_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        HIPR_CUDA(cudaFuncSetAttribute(nlm2d_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         attr = true;
     }
-    dim3 grid((unsigned)((W + NL_T - 1) / NL_T), (unsigned)((H + NL_T - 1) / NL_T));
+    dim3 grid((unsigned)((W + NL_TC - 1) / NL_TC), (unsigned)((H + NL_TR - 1) / NL_TR));
     if (grid.y > 65535) return HIPR_E_RANGE;
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == HIPR_F32)

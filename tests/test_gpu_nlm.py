@@ -6,7 +6,7 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-RTOL_NLM = 1e-12     # float64 throughout; the oracle's integral images carry ~1e-13 of their own
+RTOL_NLM = 1e-9      # float64 distances and accumulators; weights to ~4e-11 (csrc/nlm2d.cu, exp_small_neg)
 
 
 def _image(shape, seed, noise=0.03):
