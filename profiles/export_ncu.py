@@ -59,7 +59,8 @@ def main():
     for rep in reps:
         hdr, units, rows = raw_rows(rep)
         for r in rows:
-            rec = {"report": os.path.basename(rep), "kernel": r[hdr.index("Kernel Name")].split("(")[0]}
+            full = r[hdr.index("Kernel Name")]
+            rec = {"report": os.path.basename(rep), "kernel": full.split("(const")[0].split("(hipr::")[0].strip()}
             for m in METRICS:
                 if m in hdr:
                     i = hdr.index(m)
@@ -89,7 +90,9 @@ def main():
             w.writerow(rec)
     print("wrote", path, len(recs), "launches")
     # dominant kernel's DRAM traffic per launch -> bench.py's roofline.traffic
-    k1 = [r for r in recs if r["kernel"].startswith("void chansum_bulk_kernel")]
+    # (the plain float32 variant only: not the flat-field <.., true, ..> instantiation)
+    k1 = [r for r in recs if "chansum_bulk_kernel" in r["kernel"]
+          and not r["kernel"].split("chansum_bulk_kernel<")[1].split(",")[1:2] in (["1"], [" 1"], [" 1>"], [" (bool)1"])]
     if k1:
         tr = [r["dram__bytes_read.sum [byte]"] + r["dram__bytes_write.sum [byte]"] for r in k1]
         js = {"chansum_bytes_per_launch": sum(tr) / len(tr), "launches": len(tr), "source": k1[0]["report"],
