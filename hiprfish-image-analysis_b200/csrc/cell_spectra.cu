@@ -240,6 +240,12 @@ static int accumulate_launch(const float *cube, const LabelT *labels, int64_t np
     return HIPR_OK;
 }
 
+int cell_compact_launch(const int *counts, int64_t max_label, int *n_cells, long long *labels_out, long long *area_out,
+                        cudaStream_t st) {
+    cell_compact_kernel<<<1, 1024, 0, st>>>(counts, max_label, n_cells, labels_out, area_out);
+    return after_launch();
+}
+
 }  // namespace hipr
 
 using namespace hipr;
@@ -286,9 +292,7 @@ extern "C" int hipr_cell_spectra_finalize(const double *sums_dev, const int32_t 
         C <= 0 || max_label < 0)
         return HIPR_E_ARG;
     cudaStream_t st = (cudaStream_t)stream;
-    cell_compact_kernel<<<1, 1024, 0, st>>>(counts_dev, max_label, n_cells_dev, (long long *)labels_out,
-                                            (long long *)area_out);
-    int e = after_launch();
+    int e = cell_compact_launch(counts_dev, max_label, n_cells_dev, (long long *)labels_out, (long long *)area_out, st);
     if (e) return e;
     int64_t blocks = (max_label + 7) / 8;   // upper bound on the rows: one warp each
     const int64_t cap = (int64_t)sm_count() * 8;

@@ -38,6 +38,9 @@ _SIGNATURES = {
     "hipr_cell_spectra_accumulate": (_i, [_vp, _vp, _i, _i64, _i64, _i, _i64, _vp, _vp, _vp, _vp]),
     "hipr_cell_spectra_reset": (_i, [_vp, _vp, _i64, _i, _vp]),
     "hipr_cell_spectra_finalize": (_i, [_vp, _vp, _i64, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "hipr_cell_moments": (_i, [_vp, _i, _i, _i, _i64, _vp, _vp]),
+    "hipr_cell_geometry_finalize": (_i, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "hipr_paint_labels": (_i, [_vp, _i, _i64, _vp, _i, _i64, _i, _vp, _vp]),
     "hipr_neighbor2d_host": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp]),
     "hipr_neighbor2d_host_raw": (_i, [_vp, _i, C.c_double, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp]),
     "hipr_cell_spectra_host": (_i, [_vp, _vp, _i, _i64, _i64, _i, _i64, _vp, _vp, _vp, _vp, _vp]),

@@ -556,6 +556,61 @@ def cell_spectra(cube, labels, max_label=None):
     return cell_spectra_finalize(sums, counts)
 
 
+GEOMETRY_COLUMNS = ("centroid_row", "centroid_col", "major_axis_length", "minor_axis_length", "eccentricity",
+                    "orientation", "mu20", "mu02", "mu11")
+
+
+def cell_geometry(labels, max_label=None):
+    """regionprops(segmentation) geometry of a 2-D label image: -> (labels int64 (n,), area int64 (n,),
+    geometry float64 (n, 9) with columns GEOMETRY_COLUMNS), rows in ascending order of the labels present
+    (syn/hiprfish_imaging_classify_spectra.py:38-46).  Integer raw moments on the device are exact."""
+    labels = _dev(labels, "labels", (torch.int32, torch.int64))
+    if labels.dim() != 2:
+        raise ValueError("labels must be a 2-D label image")
+    if max_label is None:
+        max_label = int(label_max(labels).item())
+    max_label = int(max_label)
+    dev = labels.device
+    Hh, Ww = labels.shape
+    cap = max(max_label, 1)
+    mom = torch.empty((max_label + 1, 6), dtype=torch.int64, device=dev)
+    scratch = torch.empty(max_label + 1, dtype=torch.int32, device=dev)
+    n_cells = torch.zeros(1, dtype=torch.int32, device=dev)
+    lab = torch.empty(cap, dtype=torch.int64, device=dev)
+    area = torch.empty(cap, dtype=torch.int64, device=dev)
+    geom = torch.empty((cap, 9), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        check(lib().hipr_cell_moments(C.c_void_p(labels.data_ptr()), labels.element_size(), Hh, Ww, max_label,
+                                      C.c_void_p(mom.data_ptr()), _stream()), "cell_moments")
+        check(lib().hipr_cell_geometry_finalize(C.c_void_p(mom.data_ptr()), max_label, C.c_void_p(scratch.data_ptr()),
+                                                C.c_void_p(n_cells.data_ptr()), C.c_void_p(lab.data_ptr()),
+                                                C.c_void_p(area.data_ptr()), C.c_void_p(geom.data_ptr()), _stream()),
+              "cell_geometry_finalize")
+    n = int(n_cells.item())
+    return lab[:n], area[:n], geom[:n]
+
+
+def paint_labels(labels, values, max_label=None):
+    """out[p] = values[labels[p]]: the `image[segmentation == label] = value` loops of
+    eco/hiprfish_imaging_image_classification.py:64-70 / bio/...analysis.py:1247-1257 as one gather.
+    values: (max_label + 1,) or (max_label + 1, K) float32 / float64, row 0 = background."""
+    labels = _dev(labels, "labels", (torch.int32, torch.int64))
+    values = _dev(values, "values")
+    squeeze = values.dim() == 1
+    v2 = values.reshape(values.shape[0], -1)
+    if max_label is None:
+        max_label = v2.shape[0] - 1
+    if v2.shape[0] < max_label + 1:
+        raise ValueError("values needs max_label + 1 rows")
+    K = v2.shape[1]
+    out = torch.empty(tuple(labels.shape) + (() if squeeze else (K,)), dtype=values.dtype, device=labels.device)
+    with torch.cuda.device(labels.device):
+        check(lib().hipr_paint_labels(C.c_void_p(labels.data_ptr()), labels.element_size(), labels.numel(),
+                                      C.c_void_p(v2.data_ptr()), K, int(max_label), _DT[values.dtype],
+                                      C.c_void_p(out.data_ptr()), _stream()), "paint_labels")
+    return out
+
+
 # ---------------------------------------------------------------------------------------------
 # host-buffer (numpy) entry points: copies happen inside the library
 # ---------------------------------------------------------------------------------------------

@@ -259,6 +259,33 @@ int hipr_cell_spectra_finalize(const double *sums_dev, const int32_t *counts_dev
                                int64_t *labels_out, int64_t *area_out, double *avgint_out,
                                double *avgint_norm_out, void *stream);
 
+/* ---- per-cell geometry and paint-by-label ---------------------------------------------------
+ * hipr_cell_moments + hipr_cell_geometry_finalize replace skimage.measure.regionprops(segmentation) as
+ * syn/hiprfish_imaging_classify_spectra.py:38-46 and bio/..._analysis.py:1232-1240 read it: label, centroid,
+ * major_axis_length, minor_axis_length, eccentricity, orientation, area.
+ *   labels_dev   (H, W) int32 / int64, <= 0 background;
+ *   moments_dev  (max_label + 1, 6) uint64, zeroed by the call: count, sum r, sum c, sum r^2, sum c^2, sum r c
+ *                (integer atomics: exact and order independent; slabs of a split mosaic can be all-reduced
+ *                after offsetting rows on the host side);
+ *   finalize: counts_scratch_dev (max_label + 1) int32 scratch; n_cells_dev (1) int32; labels_out, area_out
+ *   (max_label) int64; geometry_out (max_label, 9) float64, the first n_cells rows valid, ascending label:
+ *   [centroid_row, centroid_col, major_axis_length, minor_axis_length, eccentricity, orientation,
+ *    mu20, mu02, mu11] (central moments of (row, col)).  Axis lengths and eccentricity are the eigenvalues of
+ *   the coordinate covariance (4 sqrt(l)), the same in every scikit-image version; orientation follows the
+ *   'rc' convention of scikit-image >= 0.16 (the reference does not pin its version).
+ * hipr_paint_labels replaces the `image[segmentation == label] = value` loops,
+ *   eco/hiprfish_imaging_image_classification.py:64-70, bio/..._analysis.py:1247-1257:
+ *   out_dev[p, :] = values_dev[labels_dev[p], :], values_dev (max_label + 1, K) of dtype (row 0 = background);
+ *   labels outside [0, max_label] take row 0.
+ */
+int hipr_cell_moments(const void *labels_dev, int label_bytes, int H, int W, int64_t max_label,
+                      uint64_t *moments_dev, void *stream);
+int hipr_cell_geometry_finalize(const uint64_t *moments_dev, int64_t max_label, int32_t *counts_scratch_dev,
+                                int32_t *n_cells_dev, int64_t *labels_out, int64_t *area_out,
+                                double *geometry_out, void *stream);
+int hipr_paint_labels(const void *labels_dev, int label_bytes, int64_t npix, const void *values_dev, int K,
+                      int64_t max_label, int dtype, void *out_dev, void *stream);
+
 /* ---- host-buffer entry points (what a numpy caller binds; copies are inside) --------------
  * hipr_neighbor2d_host: cube_host (H, W, C) float32 -> score_host (H, W) float32:
  *   channel sum -> /max -> edge pad -> line profiles -> epilogue `flavour`, i.e.

@@ -478,3 +478,47 @@ def neighbor2d_score(cube, flavour="F1", calibration=None, lp_func=None):
     _, padded = prologue(cube, calibration=calibration)
     lp = (lp_func or line_profile_2d_v2)(padded, 11, 9)
     return EPILOGUES[flavour](lp)
+
+
+def cell_geometry(seg):
+    """regionprops(seg) geometry (test infrastructure): for every label present, ascending: label, area,
+    and [centroid_row, centroid_col, major_axis_length, minor_axis_length, eccentricity, orientation, mu20,
+    mu02, mu11], following scikit-image's _regionprops.py: centroid = mean of the pixel coordinates; inertia
+    tensor [[mu02, -mu11], [-mu11, mu20]] / area from the central moments; its eigenvalues l1 >= l2 (clipped at
+    0) give 4 sqrt(l1), 4 sqrt(l2), sqrt(1 - l2 / l1); orientation in the 'rc' convention of scikit-image >= 0.16.
+    PARITY UNPINNED for orientation (the reference's scikit-image version is not pinned and the convention
+    changed in 0.16); the other properties are version independent.  Consumers:
+    syn/hiprfish_imaging_classify_spectra.py:38-46, bio/hiprfish_imaging_biofilm_analysis.py:1232-1240."""
+    seg = np.asarray(seg)
+    labs = np.unique(seg[seg > 0])
+    geom = np.zeros((labs.size, 9))
+    area = np.zeros(labs.size, dtype=np.int64)
+    for i, L in enumerate(labs):
+        rc = np.argwhere(seg == L).astype(np.float64)
+        area[i] = rc.shape[0]
+        cen = rc.mean(axis=0)
+        d = rc - cen
+        mu20, mu02, mu11 = (d[:, 0] ** 2).sum(), (d[:, 1] ** 2).sum(), (d[:, 0] * d[:, 1]).sum()
+        T = np.array([[mu02, -mu11], [-mu11, mu20]]) / area[i]
+        ev = np.clip(np.sort(np.linalg.eigvalsh(T))[::-1], 0, None)
+        l1, l2 = ev
+        a, b, c = T[0, 0], T[0, 1], T[1, 1]
+        if a - c == 0:
+            orient = -np.pi / 4 if b < 0 else np.pi / 4
+        else:
+            orient = 0.5 * np.arctan2(-2 * b, c - a)
+        geom[i] = [cen[0], cen[1], 4 * np.sqrt(l1), 4 * np.sqrt(l2), 0.0 if l1 == 0 else np.sqrt(1 - l2 / l1), orient,
+                   mu20, mu02, mu11]
+    return labs.astype(np.int64), area, geom
+
+
+def paint_labels(seg, values):
+    """image[seg == label] = values[label] for every label (eco/hiprfish_imaging_image_classification.py:64-70,
+    bio/hiprfish_imaging_biofilm_analysis.py:1247-1257), values[0] = background."""
+    seg = np.asarray(seg)
+    values = np.asarray(values)
+    out = np.empty(seg.shape + values.shape[1:], dtype=values.dtype)
+    out[...] = values[0]
+    for L in np.unique(seg[seg > 0]):
+        out[seg == L] = values[L]
+    return out

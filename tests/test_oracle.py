@@ -171,3 +171,18 @@ def test_nlm_properties(oracle):
     np.testing.assert_allclose(oracle.denoise_nl_means_2d(img, h=1e-4), img, rtol=1e-14)
     # even patch sizes are made odd, as skimage does
     assert np.array_equal(oracle.denoise_nl_means_2d(img, patch_size=6, h=0.05), oracle.denoise_nl_means_2d(img, patch_size=7, h=0.05))
+
+
+def test_cell_geometry_known_shapes(oracle):
+    """The regionprops restatement on shapes with closed-form moments."""
+    seg = np.zeros((30, 40), dtype=np.int64)
+    seg[5:9, 10:30] = 3            # 4 x 20 rectangle
+    lab, area, g = oracle.cell_geometry(seg)
+    assert lab.tolist() == [3] and area.tolist() == [80]
+    np.testing.assert_allclose(g[0, :2], [6.5, 19.5])
+    # variances of a discrete uniform: (n^2 - 1) / 12
+    np.testing.assert_allclose(g[0, 2], 4 * np.sqrt((20 ** 2 - 1) / 12.0))
+    np.testing.assert_allclose(g[0, 3], 4 * np.sqrt((4 ** 2 - 1) / 12.0))
+    np.testing.assert_allclose(abs(g[0, 5]), np.pi / 2)      # long axis along the columns ('rc' convention)
+    painted = oracle.paint_labels(seg, np.array([0.0, 1.0, 2.0, 7.5]))
+    assert painted[6, 12] == 7.5 and painted[0, 0] == 0.0 and painted.sum() == 80 * 7.5
