@@ -53,6 +53,7 @@ def parse():
                          "side chosen from a calibration pass so that the K timed steps take about --cpu-budget seconds)")
     ap.add_argument("--cpu-budget", type=float, default=90.0, help="target seconds of the --impl reference timed region")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--no-extras", action="store_true", help="skip the timings of the rows either side of the hot path")
     ap.add_argument("--streams", type=int, default=2,
                     help="CUDA streams consecutive (independent) FOVs alternate over; 2 lets FOV i+1's channel sum "
                          "run under FOV i's stencil")
@@ -239,6 +240,68 @@ def bind_to_gpu_cpus(index):
     except Exception as exc:      # NVML or the cpuset may not allow it: run unbound
         return "unbound (%s)" % type(exc).__name__
     return "unbound"
+
+
+def measure_next_rows(cube, labels, with_cpu):
+    """The rows either side of the hot path, device-resident, each beside its CPU restatement
+    timed on a bounded crop: registration paste + flat field + sum (K0), flat-field channel sum, NL-means
+    denoise, the denoised chain, per-cell geometry, paint by label.  Extra information, not the headline."""
+    import numpy as np
+    import torch
+    from hipr_b200 import ops
+
+    def gpu_ms(fn, n=10):
+        for _ in range(2):
+            fn()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / n
+
+    npix = cube.shape[0] * cube.shape[1]
+    edges = (0, 32, 55, 75, 89, 95)
+    stacks = [cube[:, :, a:b].contiguous() for a, b in zip(edges[:-1], edges[1:])]
+    shifts = [(0, 0), (3, -2), (-4, 5), (1, 1), (-1, -7)]
+    cal = torch.rand(cube.shape, device=cube.device) + 0.5
+    s64 = ops.channel_sum(cube, None, normalize=True, dtype=torch.float64)
+    L = int(ops.label_max(labels).item())
+    lut = torch.rand((L + 1, 3), device=cube.device, dtype=torch.float64)
+    out = {}
+    t = gpu_ms(lambda: ops.register_stacks(stacks, shifts))
+    out["register_stacks"] = {"ms": t, "gb_s": npix * 768 / t / 1e6, "bytes_per_px": 768}
+    t = gpu_ms(lambda: ops.register_stacks(stacks, shifts, cal))
+    out["register_stacks_flat_field"] = {"ms": t, "gb_s": npix * 1148 / t / 1e6, "bytes_per_px": 1148}
+    t = gpu_ms(lambda: ops.channel_sum(cube, cal, normalize=False, dtype=torch.float64, return_max=True))
+    out["channel_sum_flat_field"] = {"ms": t, "gb_s": npix * 768 / t / 1e6, "bytes_per_px": 768}
+    t = gpu_ms(lambda: ops.denoise_nl_means(s64, h=0.02), n=5)
+    out["denoise_nl_means"] = {"ms": t, "mpix_s": npix / t / 1e3}
+    t = gpu_ms(lambda: ops.neighbor2d_score(cube, "F1", denoise_h=0.02), n=5)
+    out["chain_sum_denoise_score"] = {"ms": t, "mpix_s": npix / t / 1e3}
+    t = gpu_ms(lambda: ops.cell_geometry(labels, L))
+    out["cell_geometry"] = {"ms": t, "cells": L}
+    t = gpu_ms(lambda: ops.paint_labels(labels, lut, L))
+    out["paint_labels_rgb"] = {"ms": t, "gb_s": npix * (labels.element_size() + 24) / t / 1e6}
+    if with_cpu:
+        from oracle import hipr_oracle
+        n = 512
+        crop = [st[:n, :n].cpu().numpy() for st in stacks]
+        t0 = time.perf_counter()
+        hipr_oracle.register_stacks(crop, shifts, cal[:n, :n].cpu().numpy())
+        out["register_stacks_flat_field"]["cpu_ms_scaled"] = 1e3 * (time.perf_counter() - t0) * npix / (n * n)
+        m = 160
+        t0 = time.perf_counter()
+        hipr_oracle.denoise_nl_means_2d(s64[:m, :m].cpu().numpy(), h=0.02)
+        out["denoise_nl_means"]["cpu_ms_scaled"] = 1e3 * (time.perf_counter() - t0) * npix / (m * m)
+        out["denoise_nl_means"]["cpu_note"] = "numpy restatement of skimage's fast mode on a %dx%d crop, scaled by pixels" % (m, m)
+        lab_np = labels[:n, :n].cpu().numpy()
+        t0 = time.perf_counter()
+        hipr_oracle.cell_geometry(lab_np)
+        out["cell_geometry"]["cpu_ms_scaled"] = 1e3 * (time.perf_counter() - t0) * npix / (n * n)
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -495,6 +558,8 @@ def run_b200(args):
                                      "384 B/px rate can exceed the HBM peak"},
             "gpu_launches": launches, "clocks": clocks,
         }
+        if world == 1 and not args.no_extras:
+            line["next_rows"] = measure_next_rows(cubes[0], labels[0], not args.no_cpu)
         if not args.no_cpu and world == 1:
             side = args.cpu_sample or H
             crop = cubes[0][:side, :side].cpu().numpy()

@@ -52,3 +52,24 @@ def test_paint_labels(torch_cuda, oracle, K):
     assert np.array_equal(got32.cpu().numpy(), want.astype(np.float32))
     with pytest.raises(ValueError):
         hipr_b200.paint_labels(labels.cuda(), torch_cuda.from_numpy(values[:5]).cuda(), max_label=L)
+
+
+def test_next_rows_against_frozen_vectors(torch_cuda):
+    """The CUDA path against tests/golden/next_rows_vectors.npz (no oracle code involved)."""
+    import os
+    import hipr_b200
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "next_rows_vectors.npz"))
+    cu = lambda a: torch_cuda.from_numpy(np.ascontiguousarray(a)).cuda()
+    cube, ssum, _ = hipr_b200.register_stacks([cu(g["reg_stack%d" % i]) for i in range(3)], g["reg_shifts"],
+                                              calibration=cu(g["reg_calibration"]))
+    np.testing.assert_allclose(cube.cpu().numpy(), g["reg_cube"], rtol=1.2e-7)
+    np.testing.assert_allclose(ssum.cpu().numpy(), g["reg_sum"], rtol=1e-13)
+    np.testing.assert_allclose(hipr_b200.denoise_nl_means(cu(g["nlm_in"]), h=0.02).cpu().numpy(), g["nlm_out_h002"], rtol=1e-9)
+    np.testing.assert_allclose(hipr_b200.denoise_nl_means(cu(g["nlm_in"]), h=0.1).cpu().numpy(), g["nlm_out_h01"], rtol=1e-9)
+    score = hipr_b200.lne2d(hipr_b200.denoise_nl_means(cu(g["nlm_in"]), h=0.02), "F1")
+    np.testing.assert_allclose(score.cpu().numpy(), g["nlm_score_F1"], rtol=1e-6, atol=1e-9)
+    lab, area, geom = hipr_b200.cell_geometry(cu(g["geo_seg"]))
+    assert np.array_equal(lab.cpu().numpy(), g["geo_labels"]) and np.array_equal(area.cpu().numpy(), g["geo_area"])
+    np.testing.assert_allclose(geom.cpu().numpy(), g["geo_geometry"], rtol=1e-10, atol=1e-10)
+    painted = hipr_b200.paint_labels(cu(g["geo_seg"]), cu(g["paint_values"]))
+    assert np.array_equal(painted.cpu().numpy(), g["paint_out"])

@@ -186,3 +186,17 @@ def test_cell_geometry_known_shapes(oracle):
     np.testing.assert_allclose(abs(g[0, 5]), np.pi / 2)      # long axis along the columns ('rc' convention)
     painted = oracle.paint_labels(seg, np.array([0.0, 1.0, 2.0, 7.5]))
     assert painted[6, 12] == 7.5 and painted[0, 0] == 0.0 and painted.sum() == 80 * 7.5
+
+
+def test_oracle_next_rows_match_frozen_vectors(oracle):
+    """tests/golden/next_rows_vectors.npz (make_golden_next.py): the restatements have not drifted."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "next_rows_vectors.npz"))
+    cube, ssum = oracle.register_stacks([g["reg_stack0"], g["reg_stack1"], g["reg_stack2"]], g["reg_shifts"], g["reg_calibration"])
+    assert np.array_equal(cube, g["reg_cube"]) and np.array_equal(ssum, g["reg_sum"])
+    np.testing.assert_allclose(oracle.denoise_nl_means_2d(g["nlm_in"], h=0.02), g["nlm_out_h002"], rtol=1e-13)
+    np.testing.assert_allclose(oracle.denoise_nl_means_2d(g["nlm_in"], h=0.1), g["nlm_out_h01"], rtol=1e-13)
+    lab, area, geom = oracle.cell_geometry(g["geo_seg"])
+    assert np.array_equal(lab, g["geo_labels"]) and np.array_equal(area, g["geo_area"])
+    np.testing.assert_allclose(geom, g["geo_geometry"], rtol=1e-13, atol=1e-13)
+    assert np.array_equal(oracle.paint_labels(g["geo_seg"], g["paint_values"]), g["paint_out"])
