@@ -67,6 +67,8 @@ def parse():
                     help="fov (default, the headline): one 2048^2 FOV per GPU per step; mosaic: BASELINE config 5, one "
                          "stitched mosaic split into row slabs across the ranks with an NCCL halo exchange")
     ap.add_argument("--mosaic-side", type=int, default=16384)
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="mosaic halo / range exchange: this library's kernels over NVLink peer memory, or NCCL send/recv + all-reduce")
     ap.add_argument("--zstack", default="1024x1024x64", help="X x Y x Z of the --workload zstack volume (BASELINE config 4)")
     return ap.parse_args()
 
@@ -604,18 +606,19 @@ def run_mosaic(args):
         b = min(a + 256, rows)
         cube[a:b] = synth.make_cube(b - a, side, C, seed=1234 + r0 + a, device=dev, labels=labels[a:b])
     slab = sharding.MosaicSlab()
+    scorer = sharding.P2PMosaicSlab(rows, side) if args.exchange == "p2p" else slab
 
     def barrier():
         dist.barrier()
         torch.cuda.synchronize()
 
     for _ in range(max(args.warmup, 3)):
-        slab.score(cube, "F1")
+        scorer.score(cube, "F1")
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
     for _ in range(args.steps):
-        score = slab.score(cube, "F1")
+        score = scorer.score(cube, "F1")
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -638,12 +641,17 @@ def run_mosaic(args):
             "metric": "mosaic neighbor2d Mpix/s (row slabs + NCCL halo exchange)", "value": npix * args.steps / (ms * 1e-3) / 1e6,
             "unit": "Mpix/s", "n_gpus": world, "steps": args.steps, "ms_per_step": ms / args.steps, "scaling": "strong",
             "config": {"workload": "c5: %dx%dx%d mosaic, %d row slabs of %d rows" % (side, side, C, world, rows),
-                       "halo_bytes_per_neighbour": 5 * side * 8, "flavour": "F1"},
+                       "halo_bytes_per_neighbour": 5 * side * 8, "flavour": "F1",
+                       "exchange": "own kernels over NVLink peer memory (csrc/mosaic_p2p.cu)" if args.exchange == "p2p"
+                       else "NCCL send/recv + all-reduce"},
             "frac_of_hbm_peak_per_gpu": npix / world * BYTES_PER_PIXEL / (ms / args.steps * 1e-3) / 1e9 / 6554.2,
             "cell_spectra": {"cells": int(cells[0].numel()), "ms_per_step": cms / args.steps,
                              "cells_per_s": int(cells[0].numel()) * args.steps / (cms * 1e-3),
                              "allreduce_bytes": (L + 1) * (C * 8 + 4)},
             "score_mean_rank0": float(score.mean())}), flush=True)
+    if args.exchange == "p2p":
+        scorer.check_peers()
+        scorer.close()
     dist.destroy_process_group()
 
 

@@ -100,6 +100,109 @@ class MosaicSlab:
         return self.hooks["finalize"](sums, counts)
 
 
+class P2PMosaicSlab:
+    """MosaicSlab.score with the exchange done by this library's own kernels over NVLink peer memory instead of
+    NCCL calls (csrc/mosaic_p2p.cu): the channel-sum kernel writes the slab's sums into a peer-mapped buffer, one
+    push kernel stores the 5 edge rows into the neighbours' halo rows and the slab's max / min keys into every
+    rank's table and releases a flag, one wait kernel acquires the flags and reduces the range.  torch.distributed
+    is used once, at construction, to exchange the 64-byte IPC handles and the slab heights.
+
+    One instance per (slab height, width); every rank must call score() the same number of times."""
+
+    def __init__(self, rows, width, group=None):
+        import ctypes as C
+        from ._lib import check, lib
+        self._C, self._check, self._lib = C, check, lib()
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.rows, self.width = int(rows), int(width)
+        all_rows = [None] * self.world
+        dist.all_gather_object(all_rows, self.rows, group=group)
+        self.all_rows = [int(r) for r in all_rows]
+        self.rows_max = max(self.all_rows)
+        nbytes = self._lib.hipr_mosaic_p2p_bytes(self.rows_max, self.width, self.world)
+        if nbytes <= 0:
+            raise ValueError("mosaic geometry not supported by the peer-memory exchange")
+        base = C.c_void_p()
+        check(self._lib.hipr_p2p_alloc(C.byref(base), nbytes), "p2p_alloc")
+        self._own = base
+        handle = (C.c_ubyte * 64)()
+        check(self._lib.hipr_p2p_get_handle(base, handle), "p2p_get_handle")
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle), group=group)
+        self._opened = []
+        bases = []
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                bases.append(base.value)
+                continue
+            peer = C.c_void_p()
+            buf = (C.c_ubyte * 64).from_buffer_copy(h)
+            check(self._lib.hipr_p2p_open_handle(buf, C.byref(peer)), "p2p_open_handle (rank %d)" % r)
+            self._opened.append(peer)
+            bases.append(peer.value)
+        self._bases = (C.c_void_p * self.world)(*bases)
+        self.epoch = 0
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self._keys = torch.empty(2, dtype=torch.int64, device=dev)
+        self._range = torch.empty(2, dtype=torch.int64, device=dev)
+        self._error = torch.zeros(1, dtype=torch.int32, device=dev)
+        dist.barrier(group=group)        # every rank has opened every buffer before the first push
+
+    def _rows_ptr(self, parity, with_top_halo):
+        C = self._C
+        p = C.c_void_p()
+        self._check(self._lib.hipr_mosaic_p2p_rows_ptr(self._own, self.rows_max, self.width, self.world, parity,
+                                                       int(with_top_halo), C.byref(p)), "p2p_rows_ptr")
+        return p
+
+    def score(self, cube_slab, flavour="F1"):
+        from . import tables
+        from ._lib import FLAVOURS
+        C = self._C
+        if tuple(cube_slab.shape[:2]) != (self.rows, self.width) or cube_slab.dtype != torch.float32:
+            raise ValueError("cube_slab must be (%d, %d, C) float32" % (self.rows, self.width))
+        cube_slab = cube_slab.contiguous()
+        Cn = cube_slab.shape[2]
+        self.epoch += 1
+        parity = self.epoch & 1
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        keys = C.c_void_p(self._keys.data_ptr())
+        # channel sums straight into this rank's peer-mapped buffer (rows 5 .. 5 + rows of ext[parity])
+        self._check(self._lib.hipr_chansum(C.c_void_p(cube_slab.data_ptr()), None, self.rows * self.width, Cn,
+                                           self._rows_ptr(parity, False), 1, keys, st), "channel_sum")
+        rows_up = self.all_rows[self.rank - 1] if self.rank > 0 else 0
+        self._check(self._lib.hipr_mosaic_p2p_exchange(self._bases, self.rank, self.world, self.rows, rows_up, self.rows_max,
+                                                       self.width, parity, keys, self.epoch,
+                                                       C.c_void_p(self._range.data_ptr()), C.c_void_p(self._error.data_ptr()),
+                                                       st), "mosaic_p2p_exchange")
+        n_top = HALO if self.rank > 0 else 0
+        n_bottom = HALO if self.rank + 1 < self.world else 0
+        Hs = self.rows + n_top + n_bottom
+        tab = tables.line_table_2d(11, 9)
+        out = torch.empty((Hs, self.width), dtype=torch.float32, device=cube_slab.device)
+        self._check(self._lib.hipr_lne2d_q(self._rows_ptr(parity, n_top > 0), Hs, self.width, self.width, 0, 1, 11, 9,
+                                           tab.ctypes.data_as(C.c_void_p), FLAVOURS[flavour],
+                                           C.c_void_p(self._range.data_ptr()), C.c_void_p(out.data_ptr()), st), "lne2d_q")
+        return out[n_top: Hs - n_bottom]
+
+    def check_peers(self):
+        """Raises if a wait kernel timed out on a peer's flag (synchronises)."""
+        if int(self._error.item()) != 0:
+            raise RuntimeError("a peer did not deliver its halo rows in time")
+
+    def close(self):
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)   # nobody still pushes into a buffer that is about to be freed
+        for p in self._opened:
+            self._lib.hipr_p2p_close_handle(p)
+        self._opened = []
+        if self._own is not None:
+            self._lib.hipr_p2p_free(self._own)
+            self._own = None
+
+
 def _cuda_hooks():
     from . import ops
 

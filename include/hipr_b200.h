@@ -286,6 +286,31 @@ int hipr_cell_geometry_finalize(const uint64_t *moments_dev, int64_t max_label, 
 int hipr_paint_labels(const void *labels_dev, int label_bytes, int64_t npix, const void *values_dev, int K,
                       int64_t max_label, int dtype, void *out_dev, void *stream);
 
+/* ---- split mosaic over NVLink peer memory (BASELINE config 5) -------------------------------------------
+ * The reference has no multi-GPU path; this is the exchange step of a stitched mosaic cut into row slabs, done by
+ * this library's kernels through peer-mapped memory instead of a collective library (csrc/mosaic_p2p.cu).
+ * Each rank allocates one buffer (hipr_p2p_alloc, hipr_mosaic_p2p_bytes), publishes its 64-byte IPC handle
+ * (hipr_p2p_get_handle) and opens every other rank's (hipr_p2p_open_handle).  Per exchange (same `epoch` = 1, 2, ...
+ * and parity = epoch & 1 on every rank): the caller's channel-sum kernel writes the slab's sums to
+ * hipr_mosaic_p2p_rows_ptr(..., with_top_halo = 0); hipr_mosaic_p2p_exchange pushes the 5 edge rows into the
+ * neighbours' halo rows and keys_local_dev (2 keys from hipr_chansum) into every rank's table, releases a flag,
+ * then waits (bounded; *error_dev = 1 on timeout) for every rank's flag and writes the global max / min keys to
+ * range_out_dev.  The extended image for hipr_lne2d_q starts at hipr_mosaic_p2p_rows_ptr(..., with_top_halo = rank > 0).
+ *   bases_host  HOST array of `world` device pointers: entry r = rank r's buffer as mapped in this process
+ *   rows, rows_up  height of this rank's slab and of the slab above (ignored for rank 0); rows_max = max over ranks
+ */
+int64_t hipr_mosaic_p2p_bytes(int rows_max, int W, int world);
+int hipr_p2p_alloc(void **ptr, int64_t bytes);
+int hipr_p2p_free(void *ptr);
+int hipr_p2p_get_handle(void *ptr, void *handle64);
+int hipr_p2p_open_handle(const void *handle64, void **peer_ptr);
+int hipr_p2p_close_handle(void *peer_ptr);
+int hipr_mosaic_p2p_rows_ptr(void *base, int rows_max, int W, int world, int parity, int with_top_halo,
+                             double **rows_ptr);
+int hipr_mosaic_p2p_exchange(void *const *bases_host, int rank, int world, int rows, int rows_up, int rows_max,
+                             int W, int parity, const uint64_t *keys_local_dev, uint64_t epoch,
+                             uint64_t *range_out_dev, int32_t *error_dev, void *stream);
+
 /* ---- host-buffer entry points (what a numpy caller binds; copies are inside) --------------
  * hipr_neighbor2d_host: cube_host (H, W, C) float32 -> score_host (H, W) float32:
  *   channel sum -> /max -> edge pad -> line profiles -> epilogue `flavour`, i.e.
