@@ -579,8 +579,9 @@ def run_b200(args):
 
 def run_mosaic(args):
     """BASELINE config 5: a stitched side x side x 95 mosaic cut into row slabs, one per rank.  Per step:
-    channel sum of the slab -> 5-row halo exchange of the sum image (NCCL send/recv) + all-reduce of its
-    max/min -> fixed-point stencil on the extended slab; then per-cell spectra with an all-reduce of the
+    channel sum of the slab -> 5-row halo exchange of the sum image + reduction of its max/min (--exchange p2p:
+    this library's kernels over NVLink peer memory; nccl: send/recv + all-reduce) -> fixed-point stencil on the
+    extended slab; then per-cell spectra with an all-reduce of the
     (L+1, C) partial sums and integer counts.  Extra line, not the headline metric."""
     import torch
     import torch.distributed as dist
@@ -638,7 +639,7 @@ def run_mosaic(args):
     if rank == 0:
         npix = side * side
         print(json.dumps({
-            "metric": "mosaic neighbor2d Mpix/s (row slabs + NCCL halo exchange)", "value": npix * args.steps / (ms * 1e-3) / 1e6,
+            "metric": "mosaic neighbor2d Mpix/s (row slabs + 5-row halo exchange over NVLink)", "value": npix * args.steps / (ms * 1e-3) / 1e6,
             "unit": "Mpix/s", "n_gpus": world, "steps": args.steps, "ms_per_step": ms / args.steps, "scaling": "strong",
             "config": {"workload": "c5: %dx%dx%d mosaic, %d row slabs of %d rows" % (side, side, C, world, rows),
                        "halo_bytes_per_neighbour": 5 * side * 8, "flavour": "F1",
