@@ -245,23 +245,19 @@ static int chansum_launch(const InT *cube, const float *calib, int64_t npix, int
             // (one static flag per template instantiation of this function)
             if constexpr (sizeof(InT) == 4) {
                 if (calib) {
-                    static bool attr_c = false;
+                    static std::atomic<uint64_t> attr_c{0};
                     auto kern = chansum_bulk_kernel<OutT, true, float>;
-                    if (!attr_c) {
+                    if (first_use_on_device(attr_c))
                         HIPR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM_BUDGET));
-                        attr_c = true;
-                    }
                     kern<<<(unsigned)grid, threads, smem, st>>>(cube, calib, nchunks, C, cpx, stages, groups, scale, out,
                                                                maxkey);
                 }
             }
             if (!calib) {
-                static bool attr_n = false;
+                static std::atomic<uint64_t> attr_n{0};
                 auto kern = chansum_bulk_kernel<OutT, false, InT>;
-                if (!attr_n) {
+                if (first_use_on_device(attr_n))
                     HIPR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM_BUDGET));
-                    attr_n = true;
-                }
                 kern<<<(unsigned)grid, threads, smem, st>>>(cube, nullptr, nchunks, C, cpx, stages, groups, scale, out,
                                                            maxkey);
             }

@@ -310,11 +310,9 @@ extern "C" int hipr_neighbor2d_fused(const float *cube_dev, int H, int W, int C,
 #define HIPR_FUSED_LAUNCH(FL, WS)                                                                             \
     do {                                                                                                      \
         auto kern = fused2d_kernel<FL, WS>;                                                                   \
-        static bool attr = false;                                                                             \
-        if (!attr) {                                                                                          \
+        static std::atomic<uint64_t> attr{0};                                                                 \
+        if (first_use_on_device(attr))                                                                        \
             HIPR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FU_SMEM_BUDGET)); \
-            attr = true;                                                                                      \
-        }                                                                                                     \
         kern<<<grid, FU_THREADS, smem, st>>>(cube_dev, g, score_dev, sum_dev, rg);                            \
     } while (0)
     if (flavour == HIPR_FLAVOUR_F1) {

@@ -26,6 +26,15 @@ inline int sm_count() {
     return n;
 }
 
+// cudaFuncSetAttribute is per device: true the first time the calling site runs on the current device
+// (one process per GPU is the normal deployment; a process driving several devices must still work).
+inline bool first_use_on_device(std::atomic<uint64_t> &mask) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return true;
+    const uint64_t bit = 1ull << (dev & 63);
+    return (mask.fetch_or(bit, std::memory_order_relaxed) & bit) == 0;
+}
+
 // Returns the launch error (if any) as the ABI's positive code and counts the launch.
 inline int after_launch() {
     g_launches.fetch_add(1, std::memory_order_relaxed);

@@ -299,11 +299,8 @@ static int launch_fast3d_b(const T *vol, int Xs, int Ys, int Zs, int src_off, in
     constexpr int SX = TX + L3_P - 1;
     const size_t smem = (size_t)SX * L3_SY * L3_SZ * sizeof(T);
     auto kern = lne3d_p11t72_kernel<T, FLAVOUR, MODE, TX, BAKED>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        HIPR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
-    }
+    static std::atomic<uint64_t> attr_done{0};
+    if (first_use_on_device(attr_done)) HIPR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int nzb = (Z + L3_TZ - 1) / L3_TZ, nyb = (Y + L3_TY - 1) / L3_TY, nxb = (X + TX - 1) / TX;
     if ((int64_t)nzb * nyb > 0x7fffffffLL || nxb > 65535) return HIPR_E_RANGE;
     dim3 grid((unsigned)(nzb * nyb), (unsigned)nxb);
@@ -378,11 +375,8 @@ static int launch_q3d(const SrcT *vol, int Xs, int Ys, int Zs, int src_off, int 
     constexpr int SX = TX + L3_P - 1;
     const size_t smem = (size_t)SX * L3_SY * L3_SZ * sizeof(float);
     auto kern = lne3d_q_kernel<SrcT, FLAVOUR, MODE, TX>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        HIPR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
-    }
+    static std::atomic<uint64_t> attr_done{0};
+    if (first_use_on_device(attr_done)) HIPR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int nzb = (Z + L3_TZ - 1) / L3_TZ, nyb = (Y + L3_TY - 1) / L3_TY, nxb = (X + TX - 1) / TX;
     if ((int64_t)nzb * nyb > 0x7fffffffLL || nxb > 65535) return HIPR_E_RANGE;
     dim3 grid((unsigned)(nzb * nyb), (unsigned)nxb);

@@ -186,11 +186,10 @@ extern "C" int hipr_denoise_nl_means_2d(const void *image_dev, int H, int W, int
     const int TSR = NL_TR + 2 * d + NL_N - 1, TSC = NL_TC + 2 * d + NL_N - 1, TP = TSC | 1;
     const size_t smem = ((size_t)TSR * TP + 2 * NL_HR * NL_HS) * sizeof(double);
     const double inv = 1.0 / (h * h * 49.0);
-    static bool attr = false;
-    if (!attr) {
+    static std::atomic<uint64_t> attr{0};
+    if (first_use_on_device(attr)) {
         HIPR_CUDA(cudaFuncSetAttribute(nlm2d_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         HIPR_CUDA(cudaFuncSetAttribute(nlm2d_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        attr = true;
     }
     dim3 grid((unsigned)((W + NL_TC - 1) / NL_TC), (unsigned)((H + NL_TR - 1) / NL_TR));
     if (grid.y > 65535) return HIPR_E_RANGE;

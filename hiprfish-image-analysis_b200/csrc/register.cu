@@ -217,11 +217,9 @@ extern "C" int hipr_register_stacks(const float *const *stacks_dev, const int32_
     const size_t smem = (size_t)(calib_dev ? 2 : 1) * RG_PX * C * sizeof(float);
     const int64_t ntiles = (int64_t)H * ((W + RG_PX - 1) / RG_PX);
     auto launch = [&](auto kern) -> int {
-        static bool attr = false;
-        if (!attr) {
+        static std::atomic<uint64_t> attr{0};
+        if (first_use_on_device(attr))
             HIPR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * RG_PX * RG_MAX_C * 4));
-            attr = true;
-        }
         int per_sm = 1;
         HIPR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, RG_THREADS, smem));
         if (per_sm < 1) per_sm = 1;
