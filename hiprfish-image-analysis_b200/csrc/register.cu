@@ -14,6 +14,12 @@
 // are one contiguous run of the stack.  Pass B sums
 // each pixel out of shared memory in float64 (four threads per pixel; with a flat field the same
 // reciprocal + exact-product quotient as K1, hipr_common.cuh).  Pass C streams the tile to the cube.
+//
+// Tried and removed (round 1): an interior-tile kernel that stages each excitation's run with one 1-D bulk
+// async copy (16-byte aligned start up to 3 floats early, next tile's copies in flight) and reads the staged
+// runs in place.  Correct, but slower on B200 (1.3 ms, then 2.1 ms with per-excitation unrolled passes, against
+// 0.88 ms): with the loads free, the summing and the re-interleaving of five runs of different pixel strides
+// into the (pixel, channel) order still cost ~75 issued instructions per element (ncu: 72 % issue slots).
 #include "hipr_common.cuh"
 
 namespace hipr {
@@ -216,9 +222,10 @@ extern "C" int hipr_register_stacks(const float *const *stacks_dev, const int32_
     }
     const size_t smem = (size_t)(calib_dev ? 2 : 1) * RG_PX * C * sizeof(float);
     const int64_t ntiles = (int64_t)H * ((W + RG_PX - 1) / RG_PX);
+    // (register_kernel<true> and <false> have the same function type: one flag per kernel, not per generic lambda)
+    static std::atomic<uint64_t> attr_gen[2];
     auto launch = [&](auto kern) -> int {
-        static std::atomic<uint64_t> attr{0};
-        if (first_use_on_device(attr))
+        if (first_use_on_device(attr_gen[calib_dev ? 1 : 0]))
             HIPR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * RG_PX * RG_MAX_C * 4));
         int per_sm = 1;
         HIPR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, RG_THREADS, smem));

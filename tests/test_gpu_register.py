@@ -91,3 +91,27 @@ def test_register_argument_errors(torch_cuda, oracle):
         hipr_b200.register_stacks([torch_cuda.zeros((8, 8, 200), device="cuda")])   # more than 192 channels
     with pytest.raises(ValueError):
         hipr_b200.register_stacks([a.cpu()])
+
+
+@pytest.mark.parametrize("with_cal", [False, True])
+def test_register_interior_and_border_tiles(torch_cuda, oracle, with_cal):
+    """A frame wide enough for the bulk-copy interior kernel (W % 4 == 0, several 64-pixel tiles) with shifts of
+    every residue mod 4, so that every alignment slack and both kernels (interior / border tiles) are hit."""
+    import hipr_b200
+    rng = np.random.default_rng(9)
+    H, W = 37, 448
+    stacks = _stacks(rng, H, W, CHANS)
+    for shifts in ([(0, 0), (3, -2), (-4, 5), (1, 1), (-1, -7)], [(2, 3), (0, -65), (5, 70), (-3, 2), (0, 0)],
+                   [(0, 0), (0, 0), (0, 0), (0, 0), (0, 0)]):
+        cal = (0.5 + rng.random((H, W, 95), dtype=np.float32)).astype(np.float32) if with_cal else None
+        want_cube, want_sum = oracle.register_stacks(stacks, shifts, cal)
+        cube, s, mk = hipr_b200.register_stacks([torch_cuda.from_numpy(a).cuda() for a in stacks], shifts,
+                                                calibration=None if cal is None else torch_cuda.from_numpy(cal).cuda())
+        if with_cal:
+            np.testing.assert_allclose(cube.cpu().numpy(), want_cube, rtol=1.2e-7, atol=0)
+            np.testing.assert_allclose(s.cpu().numpy(), want_sum, rtol=1e-13, atol=0)
+        else:
+            assert np.array_equal(cube.cpu().numpy(), want_cube.astype(np.float32))
+            np.testing.assert_allclose(s.cpu().numpy(), want_sum, rtol=1e-14, atol=0)
+        vmax, vmin = mk.values()
+        assert float(vmax) == s.max().item() and float(vmin) == s.min().item()
