@@ -613,13 +613,14 @@ def run_mosaic(args):
         dist.barrier()
         torch.cuda.synchronize()
 
+    kw = {"bands": args.bands if args.bands else 8} if args.exchange == "p2p" else {}
     for _ in range(max(args.warmup, 3)):
-        scorer.score(cube, "F1")
+        scorer.score(cube, "F1", **kw)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
     for _ in range(args.steps):
-        score = scorer.score(cube, "F1")
+        score = scorer.score(cube, "F1", **kw)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -643,7 +644,8 @@ def run_mosaic(args):
             "unit": "Mpix/s", "n_gpus": world, "steps": args.steps, "ms_per_step": ms / args.steps, "scaling": "strong",
             "config": {"workload": "c5: %dx%dx%d mosaic, %d row slabs of %d rows" % (side, side, C, world, rows),
                        "halo_bytes_per_neighbour": 5 * side * 8, "flavour": "F1",
-                       "exchange": "own kernels over NVLink peer memory (csrc/mosaic_p2p.cu)" if args.exchange == "p2p"
+                       "exchange": "own kernels over NVLink peer memory (csrc/mosaic_p2p.cu), %d row bands: stencil and exchange "
+                                   "under the channel sum" % kw["bands"] if args.exchange == "p2p"
                        else "NCCL send/recv + all-reduce"},
             "frac_of_hbm_peak_per_gpu": npix / world * BYTES_PER_PIXEL / (ms / args.steps * 1e-3) / 1e9 / 6554.2,
             "cell_spectra": {"cells": int(cells[0].numel()), "ms_per_step": cms / args.steps,

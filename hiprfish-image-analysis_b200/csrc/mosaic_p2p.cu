@@ -17,11 +17,44 @@
 // Two parities: a rank can be at most one exchange ahead of its neighbours (its next push follows its own
 // wait, which needs the neighbours' current flags, which they release only after their previous stencil -- same
 // stream -- has read the other parity).
+#include <mutex>
 #include "hipr_common.cuh"
 
 namespace hipr {
 
+int chansum_band(const void *cube, int sample_bytes, float scale, int64_t npix, int C, double *out,
+                 unsigned long long *maxkey, cudaStream_t st);
+int lne2d_q_rows(const void *image_dev, int Hs, int Ws, int64_t ld, int padded, int dtype, const int32_t *table_host,
+                 int flavour, const uint64_t *range_dev, float *out_dev, int y_begin, int y_end, cudaStream_t st);
+
 constexpr int MP_HALO = 5;
+constexpr int MP_MAX_BANDS = 16;
+constexpr int MP_MAX_DEVICES = 16;
+
+struct MosaicSide {
+    cudaStream_t s = nullptr;
+    cudaEvent_t start = nullptr, pushed = nullptr, done = nullptr, k1[MP_MAX_BANDS] = {};
+    bool ready = false;
+};
+static MosaicSide g_mside[MP_MAX_DEVICES];
+static std::mutex g_mside_mu;
+
+static int mosaic_side(MosaicSide **out) {
+    int dev = 0;
+    HIPR_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= MP_MAX_DEVICES) return HIPR_E_RANGE;
+    MosaicSide &sd = g_mside[dev];
+    if (!sd.ready) {
+        HIPR_CUDA(cudaStreamCreateWithFlags(&sd.s, cudaStreamNonBlocking));
+        HIPR_CUDA(cudaEventCreateWithFlags(&sd.start, cudaEventDisableTiming));
+        HIPR_CUDA(cudaEventCreateWithFlags(&sd.pushed, cudaEventDisableTiming));
+        HIPR_CUDA(cudaEventCreateWithFlags(&sd.done, cudaEventDisableTiming));
+        for (int i = 0; i < MP_MAX_BANDS; ++i) HIPR_CUDA(cudaEventCreateWithFlags(&sd.k1[i], cudaEventDisableTiming));
+        sd.ready = true;
+    }
+    *out = &sd;
+    return HIPR_OK;
+}
 constexpr int MP_MAX_WORLD = 64;
 
 struct MosaicLayout {
@@ -182,4 +215,93 @@ extern "C" int hipr_mosaic_p2p_exchange(void *const *bases_host, int rank, int w
     mosaic_wait_kernel<<<1, MP_MAX_WORLD, 0, st>>>(pb.base[rank], world, rows_max, W, parity, (unsigned long long)epoch,
                                                    timeout, reinterpret_cast<unsigned long long *>(range_out_dev), error_dev);
     return after_launch();
+}
+
+
+// One slab of a split mosaic, cube -> score, with the exchange AND the stencil hidden under the channel sum:
+// the slab is cut into row bands; the first and the last band are summed first and their edge rows pushed to
+// the neighbours; then band b + 1 is summed (HBM-bound, caller's stream) while the stencil of band b (SM-bound,
+// tile-local quantisation) runs on a side stream; the two edge bands' stencils follow the wait kernel.  F3
+// needs the global range for its epsilon and runs unbanded (sum, exchange, stencil in order).
+extern "C" int hipr_mosaic_p2p_score(const float *cube_slab_dev, int C, void *const *bases_host, int rank, int world,
+                                     int rows, int rows_up, int rows_max, int W, int parity, uint64_t epoch,
+                                     const int32_t *table_host, int flavour, int bands, uint64_t *keys_local_dev,
+                                     uint64_t *range_dev, int32_t *error_dev, float *score_dev, void *stream) {
+    if (!cube_slab_dev || !bases_host || !table_host || !keys_local_dev || !range_dev || !error_dev || !score_dev ||
+        C < 1 || world < 1 || world > MP_MAX_WORLD || rank < 0 || rank >= world || rows < MP_HALO || rows > rows_max ||
+        W < 1 || (parity != 0 && parity != 1))
+        return HIPR_E_ARG;
+    if (flavour != HIPR_FLAVOUR_F1 && flavour != HIPR_FLAVOUR_F2 && flavour != HIPR_FLAVOUR_F3) return HIPR_E_FLAVOUR;
+    cudaStream_t st = (cudaStream_t)stream;
+    const MosaicLayout l = mosaic_layout(rows_max, W, world);
+    double *ext = reinterpret_cast<double *>(bases_host[rank]) + parity * l.ext_elems;
+    double *own = ext + (int64_t)MP_HALO * W;
+    const int n_top = rank > 0 ? MP_HALO : 0, n_bottom = rank + 1 < world ? MP_HALO : 0;
+    const double *img = n_top ? ext : own;                 // the extended image the stencil reads
+    const int Hs = rows + n_top + n_bottom;
+    float *out_ext = score_dev - (int64_t)n_top * W;       // extended-image row n_top is score row 0
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(keys_local_dev);
+    HIPR_CUDA(cudaMemsetAsync(keys_local_dev, 0x00, 8, st));
+    HIPR_CUDA(cudaMemsetAsync(keys_local_dev + 1, 0xff, 8, st));
+    if (bands > MP_MAX_BANDS) bands = MP_MAX_BANDS;
+    int band_rows = bands > 1 ? (((rows + bands - 1) / bands) + 31) / 32 * 32 : rows;
+    if (flavour == HIPR_FLAVOUR_F3 || band_rows < 64) band_rows = rows;
+    const int nb = (rows + band_rows - 1) / band_rows;
+    int e;
+    if (nb < 3) {
+        if ((e = chansum_band(cube_slab_dev, 4, 1.f, (int64_t)rows * W, C, own, keys, st))) return e;
+        if ((e = hipr_mosaic_p2p_exchange(bases_host, rank, world, rows, rows_up, rows_max, W, parity, keys_local_dev, epoch,
+                                          range_dev, error_dev, stream)))
+            return e;
+        return lne2d_q_rows(img, Hs, W, W, 0, HIPR_F64, table_host, flavour, range_dev, out_ext, n_top, n_top + rows, st);
+    }
+    std::lock_guard<std::mutex> lock(g_mside_mu);
+    MosaicSide *sd = nullptr;
+    if ((e = mosaic_side(&sd))) return e;
+    auto band = [&](int b, int &r0, int &r1) {
+        r0 = b * band_rows;
+        r1 = (r0 + band_rows < rows) ? r0 + band_rows : rows;
+    };
+    auto k1 = [&](int b) -> int {
+        int r0, r1;
+        band(b, r0, r1);
+        return chansum_band(cube_slab_dev + (int64_t)r0 * W * C, 4, 1.f, (int64_t)(r1 - r0) * W, C, own + (int64_t)r0 * W, keys, st);
+    };
+    auto stencil = [&](int b) -> int {
+        int r0, r1;
+        band(b, r0, r1);
+        return lne2d_q_rows(img, Hs, W, W, 0, HIPR_F64, table_host, flavour, nullptr, out_ext, n_top + r0, n_top + r1, sd->s);
+    };
+    HIPR_CUDA(cudaEventRecord(sd->start, st));
+    HIPR_CUDA(cudaStreamWaitEvent(sd->s, sd->start, 0));
+    if ((e = k1(0))) return e;
+    if ((e = k1(nb - 1))) return e;
+    // push the edge rows (the keys are partial here and unused: F1 / F2 quantise tile by tile)
+    PeerBases pb;
+    memset(&pb, 0, sizeof(pb));
+    for (int r = 0; r < world; ++r) {
+        if (!bases_host[r]) return HIPR_E_ARG;
+        pb.base[r] = reinterpret_cast<unsigned char *>(bases_host[r]);
+    }
+    mosaic_push_kernel<<<1, 1024, 0, st>>>(pb, rank, world, rows, rows_up, rows_max, W, parity, keys, (unsigned long long)epoch);
+    if ((e = after_launch())) return e;
+    HIPR_CUDA(cudaEventRecord(sd->pushed, st));
+    for (int b = 1; b <= nb - 2; ++b) {
+        if ((e = k1(b))) return e;
+        HIPR_CUDA(cudaEventRecord(sd->k1[b], st));
+        HIPR_CUDA(cudaStreamWaitEvent(sd->s, sd->k1[b], 0));
+        if (b >= 2 && (e = stencil(b - 1))) return e;      // bands b - 2, b - 1, b exist
+    }
+    if (nb >= 3 && (e = stencil(nb - 2))) return e;         // its lower neighbour, the last band, was summed first
+    // the two edge bands need the neighbours' rows
+    HIPR_CUDA(cudaStreamWaitEvent(sd->s, sd->pushed, 0));
+    mosaic_wait_kernel<<<1, MP_MAX_WORLD, 0, sd->s>>>(pb.base[rank], world, rows_max, W, parity, (unsigned long long)epoch,
+                                                      20ll * 1000 * 1000 * 1000,
+                                                      reinterpret_cast<unsigned long long *>(range_dev), error_dev);
+    if ((e = after_launch())) return e;
+    if ((e = stencil(0))) return e;
+    if ((e = stencil(nb - 1))) return e;
+    HIPR_CUDA(cudaEventRecord(sd->done, sd->s));
+    HIPR_CUDA(cudaStreamWaitEvent(st, sd->done, 0));
+    return HIPR_OK;
 }

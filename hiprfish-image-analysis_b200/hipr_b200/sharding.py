@@ -157,7 +157,10 @@ class P2PMosaicSlab:
                                                        int(with_top_halo), C.byref(p)), "p2p_rows_ptr")
         return p
 
-    def score(self, cube_slab, flavour="F1"):
+    def score(self, cube_slab, flavour="F1", bands=0):
+        """bands >= 3 (F1 / F2): one call that also hides the stencil under the channel sum, band by band
+        (hipr_mosaic_p2p_score; every tile quantised with its own range).  bands = 0: channel sum, exchange,
+        stencil in order (bit-identical to MosaicSlab.score); F3 uses the exchanged global range."""
         from . import tables
         from ._lib import FLAVOURS
         C = self._C
@@ -169,6 +172,17 @@ class P2PMosaicSlab:
         parity = self.epoch & 1
         st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         keys = C.c_void_p(self._keys.data_ptr())
+        if bands >= 3:
+            tab = tables.line_table_2d(11, 9)
+            out = torch.empty((self.rows, self.width), dtype=torch.float32, device=cube_slab.device)
+            rows_up = self.all_rows[self.rank - 1] if self.rank > 0 else 0
+            self._check(self._lib.hipr_mosaic_p2p_score(C.c_void_p(cube_slab.data_ptr()), Cn, self._bases, self.rank,
+                                                        self.world, self.rows, rows_up, self.rows_max, self.width, parity,
+                                                        self.epoch, tab.ctypes.data_as(C.c_void_p), FLAVOURS[flavour],
+                                                        int(bands), keys, C.c_void_p(self._range.data_ptr()),
+                                                        C.c_void_p(self._error.data_ptr()), C.c_void_p(out.data_ptr()), st),
+                        "mosaic_p2p_score")
+            return out
         # channel sums straight into this rank's peer-mapped buffer (rows 5 .. 5 + rows of ext[parity])
         self._check(self._lib.hipr_chansum(C.c_void_p(cube_slab.data_ptr()), None, self.rows * self.width, Cn,
                                            self._rows_ptr(parity, False), 1, keys, st), "channel_sum")
@@ -184,7 +198,8 @@ class P2PMosaicSlab:
         out = torch.empty((Hs, self.width), dtype=torch.float32, device=cube_slab.device)
         self._check(self._lib.hipr_lne2d_q(self._rows_ptr(parity, n_top > 0), Hs, self.width, self.width, 0, 1, 11, 9,
                                            tab.ctypes.data_as(C.c_void_p), FLAVOURS[flavour],
-                                           C.c_void_p(self._range.data_ptr()), C.c_void_p(out.data_ptr()), st), "lne2d_q")
+                                           C.c_void_p(self._range.data_ptr()) if flavour not in ("F1", "F2") else None,
+                                           C.c_void_p(out.data_ptr()), st), "lne2d_q")
         return out[n_top: Hs - n_bottom]
 
     def check_peers(self):
@@ -212,7 +227,10 @@ def _cuda_hooks():
         return s, vmax, vmin
 
     def score(ext, gmax, gmin, flavour):
-        return ops.lne2d_fixed(ext, flavour, 11, 9, padded=False, range_keys=ops.MaxKey.from_values(gmax, gmin))
+        # F1 / F2 are invariant to any affine map of the image: every 32x32 tile is quantised with its own
+        # range (finer than the global one); F3's epsilon needs the global range
+        keys = ops.MaxKey.from_values(gmax, gmin) if flavour not in ("F1", "F2") else None
+        return ops.lne2d_fixed(ext, flavour, 11, 9, padded=False, range_keys=keys)
 
     return {"channel_sum": channel_sum, "score": score, "accumulate": ops.cell_spectra_accumulate,
             "finalize": ops.cell_spectra_finalize}

@@ -311,6 +311,16 @@ int hipr_mosaic_p2p_exchange(void *const *bases_host, int rank, int world, int r
                              int W, int parity, const uint64_t *keys_local_dev, uint64_t epoch,
                              uint64_t *range_out_dev, int32_t *error_dev, void *stream);
 
+/* The whole slab in one call, cube_slab_dev (rows, W, C) float32 -> score_dev (rows, W) float32, with the exchange
+ * and the stencil hidden under the channel sum: row bands, first and last band summed first and their edge rows
+ * pushed, then the channel sum of band b + 1 on `stream` while the stencil of band b runs on an internal side
+ * stream (tile-local quantisation, flavours F1 / F2); F3, or bands < 3, runs sum -> exchange -> stencil in order.
+ * keys_local_dev / range_dev: 2 uint64 of scratch each. */
+int hipr_mosaic_p2p_score(const float *cube_slab_dev, int C, void *const *bases_host, int rank, int world, int rows,
+                          int rows_up, int rows_max, int W, int parity, uint64_t epoch, const int32_t *table_host,
+                          int flavour, int bands, uint64_t *keys_local_dev, uint64_t *range_dev, int32_t *error_dev,
+                          float *score_dev, void *stream);
+
 /* ---- host-buffer entry points (what a numpy caller binds; copies are inside) --------------
  * hipr_neighbor2d_host: cube_host (H, W, C) float32 -> score_host (H, W) float32:
  *   channel sum -> /max -> edge pad -> line profiles -> epilogue `flavour`, i.e.

@@ -11,7 +11,18 @@ from conftest import PKG, ROOT
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, tmp):
+def _run_guarded(fn, rank, world, port, tmp):
+    """A rank that fails writes its traceback and exits hard: it must not sit in destroy_process_group (or leave its
+    peer in a collective) until the outer timeout."""
+    import traceback
+    try:
+        fn(rank, world, port, tmp)
+    except BaseException:
+        open(os.path.join(tmp, "fail%d.txt" % rank), "w").write(traceback.format_exc())
+        os._exit(1)
+
+
+def _worker_body(rank, world, port, tmp):
     import torch
     import torch.distributed as dist
     for p in (ROOT, PKG):
@@ -20,7 +31,7 @@ def _worker(rank, world, port, tmp):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
-    try:
+    if True:
         from hipr_b200 import sharding, synth
         from oracle import hipr_oracle as O
         Hm, Wm = 160, 256
@@ -35,20 +46,30 @@ def _worker(rank, world, port, tmp):
         assert np.array_equal(lab_out.cpu().numpy(), wl) and np.array_equal(area.cpu().numpy(), wa)
         np.testing.assert_allclose(avg.cpu().numpy(), wavg, rtol=1e-5)
         open(os.path.join(tmp, "ok%d" % rank), "w").write("ok")
-    finally:
-        dist.destroy_process_group()
+    dist.destroy_process_group()
+
+
+def _worker(rank, world, port, tmp):
+    _run_guarded(_worker_body, rank, world, port, tmp)
+
+
+def _spawn(fn, tmp_path, port):
+    import torch.multiprocessing as mp
+    try:
+        mp.spawn(fn, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    except Exception:
+        msgs = [p.read_text() for p in sorted(tmp_path.glob("fail*.txt"))]
+        pytest.fail("a rank failed:\n" + "\n".join(msgs))
 
 
 def test_mosaic_two_gpus_nccl(torch_cuda, tmp_path):
-    import torch.multiprocessing as mp
     if torch_cuda.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    port = 29700 + (os.getpid() % 1000)
-    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    _spawn(_worker, tmp_path, 29700 + (os.getpid() % 1000))
     assert all((tmp_path / ("ok%d" % r)).exists() for r in range(2))
 
 
-def _p2p_worker(rank, world, port, tmp):
+def _p2p_worker_body(rank, world, port, tmp):
     import torch
     import torch.distributed as dist
     for p in (ROOT, PKG):
@@ -57,7 +78,7 @@ def _p2p_worker(rank, world, port, tmp):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
-    try:
+    if True:
         from hipr_b200 import sharding, synth
         from oracle import hipr_oracle as O
         Hm, Wm = 161, 256                      # uneven slabs (81 / 80 rows)
@@ -73,20 +94,33 @@ def _p2p_worker(rank, world, port, tmp):
             if step == 0:
                 want = O.neighbor2d_score(cube.numpy(), "F1")[r0:r1]
                 np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-5, atol=5e-7)
+        for fl in ("F1", "F2"):                # banded: stencil and exchange under the channel sum, tile-local ranges
+            big = synth.make_fov(4 * 96 * world, Wm, 95, fov_index=31)[0]
+            b0, b1 = sharding.slab_bounds(big.shape[0], rank, world)
+            p2p_big = sharding.P2PMosaicSlab(b1 - b0, Wm)
+            for rep in range(3):
+                got_b = p2p_big.score(big[b0:b1].cuda(), fl, bands=4)
+            want_b = O.neighbor2d_score(big.numpy(), fl)[b0:b1]
+            # atol 1e-6: this FOV has one pixel (291, 86), score 1.2e-4, where the fixed-point stencil is 7.1e-7 off
+            # (a near-flat line beside a bright cell: error ~ 2 R_tile / (2^31 r_line))
+            np.testing.assert_allclose(got_b.cpu().numpy(), want_b, rtol=1e-5, atol=1e-6)
+            p2p_big.check_peers()
+            p2p_big.close()
         got3 = p2p.score(mine, "F3")            # F3 consumes the exchanged global range
         assert torch.equal(got3, nccl.score(mine, "F3"))
         p2p.check_peers()
         p2p.close()
         open(os.path.join(tmp, "p2p%d" % rank), "w").write("ok")
-    finally:
-        dist.destroy_process_group()
+    dist.destroy_process_group()
+
+
+def _p2p_worker(rank, world, port, tmp):
+    _run_guarded(_p2p_worker_body, rank, world, port, tmp)
 
 
 def test_mosaic_two_gpus_peer_memory(torch_cuda, tmp_path):
     """The library's own halo / range exchange over NVLink peer memory == the NCCL path, bit for bit."""
-    import torch.multiprocessing as mp
     if torch_cuda.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    port = 29800 + (os.getpid() % 1000)
-    mp.spawn(_p2p_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    _spawn(_p2p_worker, tmp_path, 29800 + (os.getpid() % 1000))
     assert all((tmp_path / ("p2p%d" % r)).exists() for r in range(2))
