@@ -101,8 +101,9 @@ def _p2p_worker_body(rank, world, port, tmp):
             for rep in range(3):
                 got_b = p2p_big.score(big[b0:b1].cuda(), fl, bands=4)
             want_b = O.neighbor2d_score(big.numpy(), fl)[b0:b1]
-            # atol 1e-6: this FOV has one pixel (291, 86), score 1.2e-4, where the fixed-point stencil is 7.1e-7 off
-            # (a near-flat line beside a bright cell: error ~ 2 R_tile / (2^31 r_line))
+            # atol 1e-6: this FOV has one pixel (291, 86), score 1.2e-4, where the fixed-point stencil is 7.1e-7 off:
+            # a local minimum along six of nine lines (lq = 0, uq = 8e-7), where F1's 1e-8 epsilon gives the score a
+            # sensitivity of 146 to uq (DESIGN.md section 3, K3q error bound)
             np.testing.assert_allclose(got_b.cpu().numpy(), want_b, rtol=1e-5, atol=1e-6)
             p2p_big.check_peers()
             p2p_big.close()
