@@ -283,6 +283,16 @@ def measure_next_rows(cube, labels, with_cpu):
     out["denoise_nl_means"] = {"ms": t, "mpix_s": npix / t / 1e3}
     t = gpu_ms(lambda: ops.neighbor2d_score(cube, "F1", denoise_h=0.02), n=5)
     out["chain_sum_denoise_score"] = {"ms": t, "mpix_s": npix / t / 1e3}
+    host = ops.pinned_empty(tuple(cube.shape), np.float32)
+    torch.from_numpy(host).copy_(cube.cpu())
+    score_host = ops.pinned_empty(tuple(cube.shape[:2]), np.float32)
+    ops.neighbor2d_score_host(host, "F1", out=score_host, denoise_h=0.02)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        ops.neighbor2d_score_host(host, "F1", out=score_host, denoise_h=0.02)
+    out["e2e_chain_with_denoise"] = {"ms": 1e3 * (time.perf_counter() - t0) / 3, "mpix_s": npix / ((time.perf_counter() - t0) / 3) / 1e6,
+                                     "api": "hipr_neighbor2d_host_denoise (pinned host cube -> score, lines 105-124 in full)"}
+    del host
     t = gpu_ms(lambda: ops.cell_geometry(labels, L))
     out["cell_geometry"] = {"ms": t, "cells": L}
     t = gpu_ms(lambda: ops.paint_labels(labels, lut, L))

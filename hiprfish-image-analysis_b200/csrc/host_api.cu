@@ -135,7 +135,7 @@ extern "C" int hipr_host_release_workspace(void) {
 // float32(count) / float32(scale))
 static int neighbor2d_host_impl(const void *cube_host, int sample_bytes, float scale, int H, int W, int C,
                                 int patch_size, int n_dirs, const int32_t *table_host, int flavour, float *score_host,
-                                float *sum_host) {
+                                float *sum_host, double denoise_h = 0.0) {
     if (!cube_host || !score_host || H < 1 || W < 1 || C < 1) return HIPR_E_ARG;
     Workspace &w = g_ws;
     std::lock_guard<std::mutex> lock(w.mu);
@@ -169,6 +169,28 @@ static int neighbor2d_host_impl(const void *cube_host, int sample_bytes, float s
             return e;
         HIPR_CUDA(cudaEventRecord(w.freed[slot], w.comp));
     }
+    if (denoise_h > 0.0) {
+        // syn/..._measurement.py:106-124 in full: /max -> NL-means -> float64 stencil (the denoised image is too smooth
+        // for the fixed-point grid).  aux[0] holds the sums and, behind them, the denoised image; aux[3]
+        // the float64 score.
+        double *den = sum_dev + (size_t)H * W;
+        if ((e = ws_aux(w, 3, 2 * img_bytes))) return e;
+        double *score64 = (double *)w.aux[3];
+        if ((e = hipr_normalize(sum_dev, HIPR_F64, (int64_t)H * W, (const uint64_t *)key, w.comp))) return e;
+        if ((e = hipr_denoise_nl_means_2d(sum_dev, H, W, HIPR_F64, 7, 11, denoise_h, den, w.comp))) return e;
+        if ((e = hipr_lne2d(den, H, W, W, 0, HIPR_F64, patch_size, n_dirs, table_host, flavour, nullptr, score64, w.comp)))
+            return e;
+        if ((e = hipr_normalize_cast(score64, (int64_t)H * W, nullptr, score_dev, w.comp))) return e;
+        HIPR_CUDA(cudaMemcpyAsync(score_host, score_dev, img_bytes, cudaMemcpyDeviceToHost, w.comp));
+        if (sum_host) {
+            if ((e = hipr_normalize_cast(den, (int64_t)H * W, nullptr, score_dev, w.comp))) return e;
+            HIPR_CUDA(cudaMemcpyAsync(sum_host, score_dev, img_bytes, cudaMemcpyDeviceToHost, w.comp));
+        }
+        HIPR_CUDA(cudaEventRecord(w.t1, w.comp));
+        HIPR_CUDA(cudaStreamSynchronize(w.comp));
+        HIPR_CUDA(cudaEventElapsedTime(&w.last_ms, w.t0, w.t1));
+        return HIPR_OK;
+    }
     // fixed-point stencil for the (11, 9) table every pipeline uses; float64 kernel otherwise
     e = hipr_lne2d_q(sum_dev, H, W, W, 0, HIPR_F64, patch_size, n_dirs, table_host, flavour, (const uint64_t *)key,
                      score_dev, w.comp);
@@ -195,6 +217,14 @@ static int neighbor2d_host_impl(const void *cube_host, int sample_bytes, float s
 extern "C" int hipr_neighbor2d_host(const float *cube_host, int H, int W, int C, int patch_size, int n_dirs,
                                     const int32_t *table_host, int flavour, float *score_host, float *sum_host) {
     return neighbor2d_host_impl(cube_host, 4, 1.f, H, W, C, patch_size, n_dirs, table_host, flavour, score_host, sum_host);
+}
+
+extern "C" int hipr_neighbor2d_host_denoise(const float *cube_host, int H, int W, int C, int patch_size, int n_dirs,
+                                            const int32_t *table_host, int flavour, double denoise_h, float *score_host,
+                                            float *sum_host) {
+    if (!(denoise_h > 0.0)) return HIPR_E_ARG;
+    return neighbor2d_host_impl(cube_host, 4, 1.f, H, W, C, patch_size, n_dirs, table_host, flavour, score_host, sum_host,
+                                denoise_h);
 }
 
 extern "C" int hipr_neighbor2d_host_raw(const void *cube_host, int sample_bytes, double scale, int H, int W, int C,

@@ -637,8 +637,9 @@ def pinned_empty(shape, dtype=np.float32):
     return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
 
 
-def neighbor2d_score_host(cube, flavour="F1", patch_size=11, phi_range=9, return_sum=False, out=None):
-    """numpy (H, W, C) float32 -> numpy (H, W) float32 score map, through hipr_neighbor2d_host."""
+def neighbor2d_score_host(cube, flavour="F1", patch_size=11, phi_range=9, return_sum=False, out=None, denoise_h=None):
+    """numpy (H, W, C) float32 -> numpy (H, W) float32 score map, through hipr_neighbor2d_host (denoise_h: with the
+    NL-means denoise of syn/...measurement.py:108 in the chain, hipr_neighbor2d_host_denoise)."""
     cube = np.ascontiguousarray(cube)
     if cube.dtype != np.float32:
         raise TypeError("cube must be float32, got %s" % cube.dtype)
@@ -648,6 +649,13 @@ def neighbor2d_score_host(cube, flavour="F1", patch_size=11, phi_range=9, return
     tab = tables.line_table_2d(patch_size, phi_range)
     score = out if out is not None else np.empty((H, W), dtype=np.float32)
     s = np.empty((H, W), dtype=np.float32) if return_sum else None
+    if denoise_h is not None:
+        check(lib().hipr_neighbor2d_host_denoise(cube.ctypes.data_as(C.c_void_p), H, W, Cn, tab.shape[1], tab.shape[0],
+                                                 _tab_ptr(tab), _flavour(flavour), float(denoise_h),
+                                                 score.ctypes.data_as(C.c_void_p),
+                                                 s.ctypes.data_as(C.c_void_p) if return_sum else None),
+              "neighbor2d_host_denoise")
+        return (score, s) if return_sum else score
     check(lib().hipr_neighbor2d_host(cube.ctypes.data_as(C.c_void_p), H, W, Cn, tab.shape[1], tab.shape[0],
                                      _tab_ptr(tab), _flavour(flavour), score.ctypes.data_as(C.c_void_p),
                                      s.ctypes.data_as(C.c_void_p) if return_sum else None), "neighbor2d_host")

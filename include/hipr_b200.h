@@ -335,6 +335,12 @@ int hipr_mosaic_p2p_score(const float *cube_slab_dev, int C, void *const *bases_
 int hipr_neighbor2d_host(const float *cube_host, int H, int W, int C, int patch_size,
                          int n_dirs, const int32_t *table_host, int flavour,
                          float *score_host, float *sum_host);
+/* hipr_neighbor2d_host with the denoise of syn/..._measurement.py:108 between the normalisation and the stencil
+ * (hipr_denoise_nl_means_2d, patch 7, distance 11, h = denoise_h; the float64 stencil follows): lines 105-124 in
+ * full.  sum_host (may be NULL) receives the DENOISED normalised sum image (the scripts' image_registered_sum_nl). */
+int hipr_neighbor2d_host_denoise(const float *cube_host, int H, int W, int C, int patch_size, int n_dirs,
+                                 const int32_t *table_host, int flavour, double denoise_h, float *score_host,
+                                 float *sum_host);
 /* hipr_neighbor2d_host on raw uint16 / uint8 counts (see hipr_chansum_raw): half / a quarter of the PCIe
  * traffic of the float32 cube, same score. */
 int hipr_neighbor2d_host_raw(const void *cube_host, int sample_bytes, double scale, int H, int W, int C,

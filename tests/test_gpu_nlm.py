@@ -46,6 +46,20 @@ def test_chain_sum_denoise_score(torch_cuda, oracle):
     np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-6, atol=1e-9)
 
 
+def test_host_chain_with_denoise(torch_cuda, oracle):
+    """hipr_neighbor2d_host_denoise: host cube -> score and denoised sum image, syn/..._measurement.py:105-124 in full."""
+    import hipr_b200
+    from hipr_b200 import synth
+    cube = synth.make_fov(80, 96, 95, fov_index=6)[0].numpy()
+    s = cube.astype(np.float64).sum(axis=2)
+    s = s / s.max()
+    den = oracle.denoise_nl_means_2d(s, h=0.02)
+    want = oracle.lne2d(den, "F1")
+    score, den_got = hipr_b200.neighbor2d_score_host(cube, "F1", denoise_h=0.02, return_sum=True)
+    np.testing.assert_allclose(score, want, rtol=1e-5, atol=1e-7)        # float32 output of the float64 chain
+    np.testing.assert_allclose(den_got, den, rtol=2e-7)
+
+
 def test_nlm_argument_errors(torch_cuda):
     import hipr_b200
     img = torch_cuda.rand((40, 40), device="cuda", dtype=torch_cuda.float64)
