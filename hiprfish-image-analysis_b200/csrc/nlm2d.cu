@@ -73,7 +73,7 @@ __device__ __forceinline__ double exp_small_neg(double x) {
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 2)
 nlm2d_kernel(const T *__restrict__ img, int H, int W, int d, double inv_h2s2, T *__restrict__ out) {
     extern __shared__ __align__(16) double nl_smem[];
     const int TSR = NL_TR + 2 * d + NL_N - 1;    // tile rows (83 for d = 11)
@@ -102,13 +102,18 @@ nlm2d_kernel(const T *__restrict__ img, int H, int W, int d, double inv_h2s2, T 
     for (int q = 0; q < NL_PPT; ++q) acc_w[q] = acc_v[q] = 0.0;
     const double *a_base = tile + (h_row + d) * TP + h_col + d;
     double *h_st = hb + h_row * NL_HS + h_col;
+    // the unshifted samples of this thread's 8 sums are the same for all 529 shifts: kept in registers (measured
+    // 5.76 -> 5.49 ms at 2048^2, at two CTAs per SM instead of three)
+    double a_reg[8 + NL_N - 1];
+#pragma unroll
+    for (int k = 0; k < 8 + NL_N - 1; ++k) a_reg[k] = h_on ? a_base[k] : 0.0;
     auto phase1 = [&](int tr, int tc, int which) {
         if (!h_on) return;
         const double *b = a_base + tr * TP + tc;
         double D[8 + NL_N - 1];
 #pragma unroll
         for (int k = 0; k < 8 + NL_N - 1; ++k) {
-            const double df = a_base[k] - b[k];
+            const double df = a_reg[k] - b[k];
             D[k] = df * df;
         }
         double *dst = h_st + which * (NL_HR * NL_HS);
