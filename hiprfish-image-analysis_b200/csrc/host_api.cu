@@ -346,13 +346,23 @@ extern "C" int hipr_cell_spectra_host(const float *cube_host, const void *labels
         if (band_px < 32) band_px = 32;
     }
     if ((e = ws_bands(w, (size_t)band_px * px_bytes))) return e;
+    const bool pageable = is_pageable(cube_host);
+    int copy_threads = (int)std::thread::hardware_concurrency();
+    copy_threads = copy_threads > 8 ? 8 : (copy_threads < 1 ? 1 : copy_threads);
+    if (pageable && (e = ws_stage(w, (size_t)band_px * px_bytes))) return e;
     int b = 0;
     for (int64_t p0 = 0; p0 < npix; p0 += band_px, ++b) {
         const int64_t np = (npix - p0 < band_px) ? npix - p0 : band_px;
         const int slot = b % NBUF;
+        const void *src = cube_host + p0 * C;
+        if (pageable) {
+            if (b >= NBUF) HIPR_CUDA(cudaEventSynchronize(w.staged_out[slot]));
+            parallel_copy(w.stage[slot], src, (size_t)np * px_bytes, copy_threads);
+            src = w.stage[slot];
+        }
         if (b >= NBUF) HIPR_CUDA(cudaStreamWaitEvent(w.copy, w.freed[slot], 0));
-        HIPR_CUDA(cudaMemcpyAsync(w.band[slot], cube_host + p0 * C, (size_t)np * px_bytes, cudaMemcpyHostToDevice,
-                                  w.copy));
+        HIPR_CUDA(cudaMemcpyAsync(w.band[slot], src, (size_t)np * px_bytes, cudaMemcpyHostToDevice, w.copy));
+        if (pageable) HIPR_CUDA(cudaEventRecord(w.staged_out[slot], w.copy));
         HIPR_CUDA(cudaEventRecord(w.copied[slot], w.copy));
         HIPR_CUDA(cudaStreamWaitEvent(w.comp, w.copied[slot], 0));
         if ((e = hipr_cell_spectra_accumulate((const float *)w.band[slot], (const char *)labels_dev + p0 * label_bytes,
