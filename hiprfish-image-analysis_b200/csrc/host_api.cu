@@ -259,8 +259,11 @@ static int neighbor2d_host_impl(const void *cube_host, int sample_bytes, float s
         return HIPR_OK;
     }
     // fixed-point stencil for the (11, 9) table every pipeline uses; float64 kernel otherwise
-    e = hipr_lne2d_q(sum_dev, H, W, W, 0, HIPR_F64, patch_size, n_dirs, table_host, flavour, (const uint64_t *)key,
-                     score_dev, w.comp);
+    // (F1 / F2: every tile quantised with its own range, the finest grid and the same as the device-resident
+    // pipeline, bit for bit; F3's epsilon needs the global range)
+    const bool tile_local = (flavour == HIPR_FLAVOUR_F1 || flavour == HIPR_FLAVOUR_F2);
+    e = hipr_lne2d_q(sum_dev, H, W, W, 0, HIPR_F64, patch_size, n_dirs, table_host, flavour,
+                     tile_local ? nullptr : (const uint64_t *)key, score_dev, w.comp);
     if (e == HIPR_E_TABLE && !(patch_size == 11 && n_dirs == 9)) {
         // general parameters: float64 stencil into the upper half of aux[0], then cast
         double *score64 = sum_dev + (size_t)H * W;
