@@ -505,6 +505,16 @@ def run_b200(args):
     torch.cuda.synchronize()
     e2e_wall_ms = 1e3 * (time.perf_counter() - t0)
     score_check = float(score_host.mean())
+    # per-cell spectra end to end: pinned host cube + host label image -> cell table on the host
+    labels_host = labels[0].cpu().numpy()
+    ops.cell_spectra_host(host, labels_host)
+    barrier()
+    t0 = time.perf_counter()
+    cell_e2e_steps = 3
+    for _ in range(cell_e2e_steps):
+        cell_tab = ops.cell_spectra_host(host, labels_host)
+    cell_e2e_ms = 1e3 * (time.perf_counter() - t0) / cell_e2e_steps
+    cell_e2e_n = int(cell_tab[0].size)
     # the same FOV as the uint16 counts a detector delivers (value = count / 65535 in float32, bioformats' rescale)
     raw = ops.pinned_empty((H, W, C), np.uint16)
     cmax = float(cubes[0].max())
@@ -520,12 +530,12 @@ def run_b200(args):
     del raw
 
     # ---- reduce over ranks (max time) -----------------------------------------------------------
-    t = torch.tensor([ms, cell_ms, e2e_dev_ms, e2e_wall_ms, k1_ms, raw_dev_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, cell_ms, e2e_dev_ms, e2e_wall_ms, k1_ms, raw_dev_ms, cell_e2e_ms], dtype=torch.float64, device=dev)
     cnt = torch.tensor([launches, cells_per_step], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    ms, cell_ms, e2e_dev_ms, e2e_wall_ms, k1_ms, raw_dev_ms = [float(x) for x in t.tolist()]
+    ms, cell_ms, e2e_dev_ms, e2e_wall_ms, k1_ms, raw_dev_ms, cell_e2e_ms = [float(x) for x in t.tolist()]
     launches, cells_all = int(cnt[0].item()), float(cnt[1].item())
 
     if rank == 0:
@@ -564,6 +574,9 @@ def run_b200(args):
                              "mpix_per_s": world * npix * args.steps / (cell_ms * 1e-3) / 1e6,
                              "ms_per_step": cell_ms / args.steps, "cells_per_fov": cells_all / world,
                              "foreground_fraction": fg_frac,
+                             "e2e": {"cells_per_s": world * cell_e2e_n / (cell_e2e_ms * 1e-3), "ms_per_step": cell_e2e_ms,
+                                     "h2d_bytes_per_step": npix * C * 4 + npix * labels[0].element_size(),
+                                     "api": "hipr_cell_spectra_host (pinned host cube + label image -> cell table, wall clock)"},
                              "algorithmic_gbs": npix * BYTES_PER_PIXEL / (cell_ms / args.steps * 1e-3) / 1e9,
                              "frac_of_hbm_peak": npix * BYTES_PER_PIXEL / (cell_ms / args.steps * 1e-3) / 1e9 / hbm_peak,
                              "note": "background pixels' channel vectors are never fetched, so the algorithmic "

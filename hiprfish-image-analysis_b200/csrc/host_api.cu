@@ -31,6 +31,9 @@ struct Workspace {
     void *stage[NBUF] = {};
     size_t stage_bytes = 0;
     cudaEvent_t staged_out[NBUF] = {};   // the H2D copy out of stage[i] has completed
+    // the cell table of the last hipr_cell_spectra_host call stays in aux[5] for hipr_cell_spectra_host_fetch
+    int64_t last_cells = -1, last_max_label = 0;
+    int last_C = 0;
     bool ready = false;
 };
 static Workspace g_ws;
@@ -391,8 +394,34 @@ extern "C" int hipr_cell_spectra_host(const float *cube_host, const void *labels
     HIPR_CUDA(cudaMemcpyAsync(&n, n_dev, 4, cudaMemcpyDeviceToHost, w.comp));
     HIPR_CUDA(cudaStreamSynchronize(w.comp));
     *n_cells = n;
+    w.last_cells = n;
+    w.last_max_label = max_label;
+    w.last_C = C;
+    if (n > capacity) return HIPR_E_RANGE;     // the table stays on the device: hipr_cell_spectra_host_fetch
+    if (n == 0) return HIPR_OK;
+    HIPR_CUDA(cudaMemcpyAsync(labels_out, lab_dev, (size_t)n * 8, cudaMemcpyDeviceToHost, w.comp));
+    HIPR_CUDA(cudaMemcpyAsync(area_out, area_dev, (size_t)n * 8, cudaMemcpyDeviceToHost, w.comp));
+    HIPR_CUDA(cudaMemcpyAsync(avgint_out, avg_dev, (size_t)n * row_bytes, cudaMemcpyDeviceToHost, w.comp));
+    HIPR_CUDA(cudaMemcpyAsync(avgint_norm_out, norm_dev, (size_t)n * row_bytes, cudaMemcpyDeviceToHost, w.comp));
+    HIPR_CUDA(cudaStreamSynchronize(w.comp));
+    return HIPR_OK;
+}
+
+extern "C" int hipr_cell_spectra_host_fetch(int64_t capacity, int64_t *labels_out, int64_t *area_out, double *avgint_out,
+                                            double *avgint_norm_out) {
+    if (!labels_out || !area_out || !avgint_out || !avgint_norm_out) return HIPR_E_ARG;
+    Workspace &w = g_ws;
+    std::lock_guard<std::mutex> lock(w.mu);
+    if (w.last_cells < 0 || !w.aux[5]) return HIPR_E_ARG;      // no table to fetch
+    const int64_t n = w.last_cells, max_label = w.last_max_label;
     if (n > capacity) return HIPR_E_RANGE;
     if (n == 0) return HIPR_OK;
+    const size_t row_bytes = (size_t)w.last_C * 8;
+    char *fin = (char *)w.aux[5];
+    int64_t *lab_dev = (int64_t *)(fin + 16);
+    int64_t *area_dev = lab_dev + max_label;
+    double *avg_dev = (double *)(area_dev + max_label);
+    double *norm_dev = avg_dev + (size_t)max_label * w.last_C;
     HIPR_CUDA(cudaMemcpyAsync(labels_out, lab_dev, (size_t)n * 8, cudaMemcpyDeviceToHost, w.comp));
     HIPR_CUDA(cudaMemcpyAsync(area_out, area_dev, (size_t)n * 8, cudaMemcpyDeviceToHost, w.comp));
     HIPR_CUDA(cudaMemcpyAsync(avgint_out, avg_dev, (size_t)n * row_bytes, cudaMemcpyDeviceToHost, w.comp));

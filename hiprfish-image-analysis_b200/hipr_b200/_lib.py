@@ -54,6 +54,7 @@ _SIGNATURES = {
     "hipr_neighbor2d_host_denoise": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, C.c_double, _vp, _vp]),
     "hipr_neighbor2d_host_raw": (_i, [_vp, _i, C.c_double, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp]),
     "hipr_cell_spectra_host": (_i, [_vp, _vp, _i, _i64, _i64, _i, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "hipr_cell_spectra_host_fetch": (_i, [_i64, _vp, _vp, _vp, _vp]),
     "hipr_host_last_elapsed_ms": (C.c_double, []),
     "hipr_host_alloc": (_i, [C.POINTER(_vp), _i64]),
     "hipr_host_free": (_i, [_vp]),

@@ -691,21 +691,24 @@ def cell_spectra_host(cube, labels):
     npix = labels.size
     if cube.size != npix * Cn:
         raise ValueError("cube and labels do not match")
-    cap = 1024
-    while True:
-        n = C.c_int64(0)
-        lab = np.empty(cap, np.int64)
-        area = np.empty(cap, np.int64)
-        avg = np.empty((cap, Cn), np.float64)
-        norm = np.empty((cap, Cn), np.float64)
-        code = lib().hipr_cell_spectra_host(cube.ctypes.data_as(C.c_void_p), labels.ctypes.data_as(C.c_void_p),
-                                            labels.itemsize, npix, labels.shape[-1] if labels.ndim > 1 else 0, Cn, cap,
-                                            C.byref(n),
-                                            lab.ctypes.data_as(C.c_void_p), area.ctypes.data_as(C.c_void_p),
-                                            avg.ctypes.data_as(C.c_void_p), norm.ctypes.data_as(C.c_void_p))
-        if code == -7 and n.value > cap:
-            cap = int(n.value)
-            continue
-        check(code, "cell_spectra_host")
-        k = int(n.value)
-        return lab[:k], area[:k], avg[:k], norm[:k]
+    cap = 4096
+
+    def alloc(k):
+        return np.empty(k, np.int64), np.empty(k, np.int64), np.empty((k, Cn), np.float64), np.empty((k, Cn), np.float64)
+
+    n = C.c_int64(0)
+    lab, area, avg, norm = alloc(cap)
+    code = lib().hipr_cell_spectra_host(cube.ctypes.data_as(C.c_void_p), labels.ctypes.data_as(C.c_void_p),
+                                        labels.itemsize, npix, labels.shape[-1] if labels.ndim > 1 else 0, Cn, cap,
+                                        C.byref(n),
+                                        lab.ctypes.data_as(C.c_void_p), area.ctypes.data_as(C.c_void_p),
+                                        avg.ctypes.data_as(C.c_void_p), norm.ctypes.data_as(C.c_void_p))
+    if code == -7 and n.value > cap:
+        # more cells than the first guess: the table is still on the device, fetch it (no second pass over the cube)
+        cap = int(n.value)
+        lab, area, avg, norm = alloc(cap)
+        code = lib().hipr_cell_spectra_host_fetch(cap, lab.ctypes.data_as(C.c_void_p), area.ctypes.data_as(C.c_void_p),
+                                                  avg.ctypes.data_as(C.c_void_p), norm.ctypes.data_as(C.c_void_p))
+    check(code, "cell_spectra_host")
+    k = int(n.value)
+    return lab[:k], area[:k], avg[:k], norm[:k]

@@ -351,6 +351,10 @@ int hipr_cell_spectra_host(const float *cube_host, const void *labels_host, int 
                            int64_t *n_cells,
                            int64_t *labels_out, int64_t *area_out, double *avgint_out,
                            double *avgint_norm_out);
+/* After hipr_cell_spectra_host returned HIPR_E_RANGE (*n_cells > capacity): copies that call's table, still on the
+ * device, into arrays of sufficient capacity without recomputing it. */
+int hipr_cell_spectra_host_fetch(int64_t capacity, int64_t *labels_out, int64_t *area_out, double *avgint_out,
+                                 double *avgint_norm_out);
 /* device-clock duration (CUDA events: before the first H2D .. after the last D2H) of the most
  * recent hipr_neighbor2d_host call in this process, in ms; negative if none yet */
 double hipr_host_last_elapsed_ms(void);

@@ -105,3 +105,21 @@ def test_cell_spectra_host_entry(torch_cuda, oracle):
     cube, lab, _ = synth.make_fov(150, 222, 95, fov_index=7, label_dtype=torch_cuda.int64)
     got = hipr_b200.cell_spectra_host(cube.numpy(), lab.numpy())
     _check(oracle, got, cube.numpy(), lab.numpy())
+
+
+def test_host_entry_point_more_cells_than_first_capacity(torch_cuda, oracle):
+    """More cells than the wrapper's first guess (4096): the table is fetched from the device without a second
+    pass (hipr_cell_spectra_host_fetch)."""
+    import hipr_b200
+    rng = np.random.default_rng(8)
+    H, W, Cn = 96, 128, 7
+    labels = np.zeros((H, W), dtype=np.int32)
+    ids = rng.permutation(H * W)[:6000]
+    labels.reshape(-1)[ids] = np.arange(1, 6001, dtype=np.int32) * 3        # non-contiguous ids, one pixel each
+    labels[10:14, 10:30] = 7                                                # and one larger cell
+    cube = rng.random((H, W, Cn), dtype=np.float32)
+    lab, area, avg, norm = hipr_b200.cell_spectra_host(cube, labels)
+    wl, wa, wavg, wnorm = oracle.cell_spectra(labels, cube)
+    assert lab.size > 4096 and np.array_equal(lab, wl) and np.array_equal(area, wa)
+    np.testing.assert_allclose(avg, wavg, rtol=1e-5)
+    np.testing.assert_allclose(norm, wnorm, rtol=1e-5)
