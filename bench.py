@@ -557,7 +557,12 @@ def run_b200(args):
             "pipeline_frac_of_hbm_peak": value / world * 1e6 * BYTES_PER_PIXEL / 1e9 / hbm_peak,
             "roofline": {"bound": "hbm", "kernel": "fused2d_kernel" if args.path == "fused" else "chansum_bulk_kernel",
                          "how": "this kernel launched alone K times between two CUDA events, same inputs",
-                         "share_of_serial_step": k1_ms / (ms / args.steps) if args.streams == 1 else None, "achieved": k1_gbs, "peak": hbm_peak,
+                         "share_of_serial_step": k1_ms / (ms / args.steps) if args.streams == 1 else None,
+                         "share_of_step": min(1.0, k1_ms / (ms / args.steps)),
+                         "share_note": "two streams: the stencil of FOV i runs under the channel sum of FOV i+1, so the step is "
+                                       "~one channel sum; ncu's serialised launch list gives 0.77 (profiles/r01_summary.md), "
+                                       "--streams 1 gives 0.74" if args.streams > 1 else "streams=1: serial step",
+                         "achieved": k1_gbs, "peak": hbm_peak,
                          "unit": "GB/s", "frac": k1_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": npix * BYTES_PER_PIXEL, "ms_per_launch": k1_ms},
             "e2e": {"value": world * npix * e2e_steps / (e2e_dev_ms * 1e-3) / 1e6, "unit": "Mpix/s",
