@@ -147,3 +147,25 @@ def test_synthetic_fov_is_deterministic_and_documented():
     assert not (a == c).all()
     ld, _ = synth.make_labels(128, 192, drop_fraction=0.3)
     assert len(ld.unique()) - 1 < (128 // 26) * (192 // 44)
+
+
+def test_mosaic_peer_buffer_layout_and_argument_checks():
+    """Host-only entry points of the peer-memory mosaic exchange: buffer size arithmetic and argument validation
+    (no device call is made)."""
+    import hipr_b200
+    lib = hipr_b200.lib()
+    rows, W, world = 2048, 16384, 8
+    ext = 2 * (rows + 10) * W * 8                  # two parities of the extended float64 sum image
+    keys = 2 * world * 2 * 8
+    flags = world * 8
+    want = -(-(ext + keys + flags) // 256) * 256
+    assert lib.hipr_mosaic_p2p_bytes(rows, W, world) == want
+    assert lib.hipr_mosaic_p2p_bytes(4, W, world) < 0          # a slab must hold the 5 halo rows it sends
+    assert lib.hipr_mosaic_p2p_bytes(rows, W, 65) < 0
+    assert lib.hipr_p2p_alloc(None, 1024) == -1
+    assert lib.hipr_p2p_get_handle(None, None) == -1
+    assert lib.hipr_p2p_open_handle(None, None) == -1
+    assert lib.hipr_p2p_free(None) == 0 and lib.hipr_p2p_close_handle(None) == 0
+    assert lib.hipr_cell_spectra_host_fetch(0, None, None, None, None) == -1
+    assert lib.hipr_register_stacks(None, None, None, None, 0, 1, 1, None, None, None, None, None) == -1
+    assert lib.hipr_denoise_nl_means_2d(None, 64, 64, 1, 7, 11, 0.02, None, None) == -1
