@@ -65,10 +65,17 @@ def allreduce_range(vmax, vmin, group=None):
     return t[0:1].clone(), (-t[1:2]).clone()
 
 
-def allreduce_cells(sums, counts, group=None):
-    """Sum the per-slab (L+1, C) float64 channel sums and (L+1) int32 pixel counts in place."""
-    dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
-    dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
+def allreduce_cells(sums, counts, group=None, root=None):
+    """Sum the per-slab (L+1, C) float64 channel sums and (L+1) int32 pixel counts in place: on every rank
+    (root=None, all-reduce) or on rank `root` only (reduce: half the traffic; the other ranks' buffers are then
+    partial sums and must not be used)."""
+    if root is None:
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
+    else:
+        dst = root if group is None else dist.get_global_rank(group, root)
+        dist.reduce(sums, dst=dst, op=dist.ReduceOp.SUM, group=group)
+        dist.reduce(counts, dst=dst, op=dist.ReduceOp.SUM, group=group)
     return sums, counts
 
 
@@ -94,9 +101,13 @@ class MosaicSlab:
         full = self.hooks["score"](ext, gmax, gmin, flavour)
         return full[n_top: full.shape[0] - n_bottom]
 
-    def cell_spectra(self, cube_slab, labels_slab, max_label):
+    def cell_spectra(self, cube_slab, labels_slab, max_label, root=None):
+        """The mosaic's cell table on every rank (root=None), or on rank `root` only (None elsewhere): the scripts
+        write one table, and a reduce moves half the bytes of an all-reduce."""
         sums, counts = self.hooks["accumulate"](cube_slab, labels_slab, max_label)
-        allreduce_cells(sums, counts, self.group)
+        allreduce_cells(sums, counts, self.group, root)
+        if root is not None and dist.get_rank(self.group) != root:
+            return None
         return self.hooks["finalize"](sums, counts)
 
 

@@ -80,6 +80,12 @@ def _worker(rank, world, port, tmp):
         # per-cell spectra: all-reduced partial sums/counts == the unsplit reduction; counts exact
         lab_out, area, avg, norm = slab.cell_spectra(cube[r0:r1], labels[r0:r1], L)
         wl, wa, wavg, wnorm = O.cell_spectra(labels.numpy(), cube.numpy())
+        rooted = slab.cell_spectra(cube[r0:r1], labels[r0:r1], L, root=world - 1)     # reduce to one rank only
+        if rank == world - 1:
+            assert np.array_equal(rooted[0], wl) and np.array_equal(rooted[1], wa)
+            np.testing.assert_allclose(rooted[2], wavg, rtol=1e-12)
+        else:
+            assert rooted is None
         assert np.array_equal(lab_out, wl) and np.array_equal(area, wa)
         np.testing.assert_allclose(avg, wavg, rtol=1e-12)
         # FOV sharding needs no communication: every FOV is scored by exactly one rank
