@@ -292,6 +292,71 @@ extern "C" int hipr_neighbor2d_host(const float *cube_host, int H, int W, int C,
     return neighbor2d_host_impl(cube_host, 4, 1.f, H, W, C, patch_size, n_dirs, table_host, flavour, score_host, sum_host);
 }
 
+// 3-D: cube_host (X, Y, Z, C) float32 -> score_host (X, Y, Z) float32: channel sum -> /max -> edge pad -> 72 x 11 line
+// profiles -> epilogue, bio/..._analysis.py:807-817 (ME2), :900-917 (F2), :1102-1125 (F3), the cube streamed in bands
+// of whole x-planes under the channel sum.
+extern "C" int hipr_neighbor3d_host(const float *cube_host, int X, int Y, int Z, int C, int patch_size, int n_dirs,
+                                    const int32_t *table_host, int flavour, float *score_host) {
+    if (!cube_host || !score_host || !table_host || X < 1 || Y < 1 || Z < 1 || C < 1) return HIPR_E_ARG;
+    Workspace &w = g_ws;
+    std::lock_guard<std::mutex> lock(w.mu);
+    int e = ws_init(w);
+    if (e) return e;
+    const int64_t plane_px = (int64_t)Y * Z, plane_bytes = plane_px * C * 4, nvox = (int64_t)X * plane_px;
+    const int planes = band_rows(plane_bytes, X);
+    if ((e = ws_bands(w, (size_t)planes * plane_bytes))) return e;
+    if ((e = ws_aux(w, 0, (size_t)nvox * 8))) return e;     // float64 sum volume
+    if ((e = ws_aux(w, 1, (size_t)nvox * 4))) return e;     // score
+    if ((e = ws_aux(w, 2, 64))) return e;
+    double *sum_dev = (double *)w.aux[0];
+    float *score_dev = (float *)w.aux[1];
+    unsigned long long *key = (unsigned long long *)w.aux[2];
+    HIPR_CUDA(cudaEventRecord(w.t0, w.copy));
+    HIPR_CUDA(cudaStreamWaitEvent(w.comp, w.t0, 0));
+    HIPR_CUDA(cudaMemsetAsync(key, 0x00, 8, w.comp));
+    HIPR_CUDA(cudaMemsetAsync(key + 1, 0xff, 8, w.comp));
+    const bool pageable = is_pageable(cube_host);
+    int copy_threads = (int)std::thread::hardware_concurrency();
+    copy_threads = copy_threads > 8 ? 8 : (copy_threads < 1 ? 1 : copy_threads);
+    if (pageable && (e = ws_stage(w, (size_t)planes * plane_bytes))) return e;
+    int b = 0;
+    for (int x0 = 0; x0 < X; x0 += planes, ++b) {
+        const int nx = (X - x0 < planes) ? X - x0 : planes;
+        const int slot = b % NBUF;
+        const void *src = (const char *)cube_host + (int64_t)x0 * plane_bytes;
+        if (pageable) {
+            if (b >= NBUF) HIPR_CUDA(cudaEventSynchronize(w.staged_out[slot]));
+            parallel_copy(w.stage[slot], src, (size_t)nx * plane_bytes, copy_threads);
+            src = w.stage[slot];
+        }
+        if (b >= NBUF) HIPR_CUDA(cudaStreamWaitEvent(w.copy, w.freed[slot], 0));
+        HIPR_CUDA(cudaMemcpyAsync(w.band[slot], src, (size_t)nx * plane_bytes, cudaMemcpyHostToDevice, w.copy));
+        if (pageable) HIPR_CUDA(cudaEventRecord(w.staged_out[slot], w.copy));
+        HIPR_CUDA(cudaEventRecord(w.copied[slot], w.copy));
+        HIPR_CUDA(cudaStreamWaitEvent(w.comp, w.copied[slot], 0));
+        if ((e = chansum_band(w.band[slot], 4, 1.f, (int64_t)nx * plane_px, C, sum_dev + (int64_t)x0 * plane_px, key, w.comp)))
+            return e;
+        HIPR_CUDA(cudaEventRecord(w.freed[slot], w.comp));
+    }
+    // fixed-point stencil for the reference's (11, 9, 9) table; the float64 stencil for any other table
+    e = hipr_lne3d_q(sum_dev, X, Y, Z, 0, HIPR_F64, patch_size, n_dirs, table_host, flavour, 0, (const uint64_t *)key,
+                     score_dev, w.comp);
+    if (e == HIPR_E_UNSUPPORTED) {
+        if ((e = ws_aux(w, 3, (size_t)nvox * 8))) return e;
+        double *score64 = (double *)w.aux[3];
+        if ((e = hipr_lne3d(sum_dev, X, Y, Z, 0, HIPR_F64, patch_size, n_dirs, table_host, flavour, (const uint64_t *)key,
+                            score64, w.comp)))
+            return e;
+        e = hipr_normalize_cast(score64, nvox, nullptr, score_dev, w.comp);
+    }
+    if (e) return e;
+    HIPR_CUDA(cudaMemcpyAsync(score_host, score_dev, (size_t)nvox * 4, cudaMemcpyDeviceToHost, w.comp));
+    HIPR_CUDA(cudaEventRecord(w.t1, w.comp));
+    HIPR_CUDA(cudaStreamSynchronize(w.comp));
+    HIPR_CUDA(cudaEventElapsedTime(&w.last_ms, w.t0, w.t1));
+    return HIPR_OK;
+}
+
 extern "C" int hipr_neighbor2d_host_denoise(const float *cube_host, int H, int W, int C, int patch_size, int n_dirs,
                                             const int32_t *table_host, int flavour, double denoise_h, float *score_host,
                                             float *sum_host) {

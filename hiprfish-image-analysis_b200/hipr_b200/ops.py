@@ -662,6 +662,23 @@ def neighbor2d_score_host(cube, flavour="F1", patch_size=11, phi_range=9, return
     return (score, s) if return_sum else score
 
 
+def neighbor3d_score_host(cube, flavour="ME2", patch_size=11, theta_range=9, phi_range=9, out=None):
+    """numpy (X, Y, Z, C) float32 -> numpy (X, Y, Z) float32 score volume, through hipr_neighbor3d_host
+    (bio/...analysis.py:807-817 for 'ME2')."""
+    cube = np.ascontiguousarray(cube)
+    if cube.dtype != np.float32:
+        raise TypeError("cube must be float32, got %s" % cube.dtype)
+    if cube.ndim != 4:
+        raise ValueError("cube must be (X, Y, Z, C)")
+    X, Y, Z, Cn = cube.shape
+    tab = tables.line_table_3d(patch_size, theta_range, phi_range)
+    score = out if out is not None else np.empty((X, Y, Z), dtype=np.float32)
+    check(lib().hipr_neighbor3d_host(cube.ctypes.data_as(C.c_void_p), X, Y, Z, Cn, tab.shape[1], tab.shape[0],
+                                     _tab_ptr(tab), _flavour(flavour), score.ctypes.data_as(C.c_void_p)),
+          "neighbor3d_host")
+    return score
+
+
 def neighbor2d_score_host_raw(cube, scale, flavour="F1", patch_size=11, phi_range=9, out=None):
     """numpy (H, W, C) uint16 / uint8 raw counts -> numpy (H, W) float32 score map, the score of the cube
     bioformats' rescale would produce (count / scale in float32), through hipr_neighbor2d_host_raw."""

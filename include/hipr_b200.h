@@ -335,6 +335,11 @@ int hipr_mosaic_p2p_score(const float *cube_slab_dev, int C, void *const *bases_
 int hipr_neighbor2d_host(const float *cube_host, int H, int W, int C, int patch_size,
                          int n_dirs, const int32_t *table_host, int flavour,
                          float *score_host, float *sum_host);
+/* hipr_neighbor3d_host: cube_host (X, Y, Z, C) float32 -> score_host (X, Y, Z) float32: channel sum -> /max -> edge
+ * pad -> 3-D line profiles -> epilogue `flavour` (ME2: bio/..._analysis.py:807-817; F2: :900-917; F3: :1102-1125),
+ * the cube streamed to the device in bands of x-planes under the channel sum. */
+int hipr_neighbor3d_host(const float *cube_host, int X, int Y, int Z, int C, int patch_size, int n_dirs,
+                         const int32_t *table_host, int flavour, float *score_host);
 /* hipr_neighbor2d_host with the denoise of syn/..._measurement.py:108 between the normalisation and the stencil
  * (hipr_denoise_nl_means_2d, patch 7, distance 11, h = denoise_h; the float64 stencil follows): lines 105-124 in
  * full.  sum_host (may be NULL) receives the DENOISED normalised sum image (the scripts' image_registered_sum_nl). */

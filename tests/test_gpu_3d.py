@@ -140,3 +140,20 @@ def test_lne3d_fixed_point_dirs_and_pipeline(torch_cuda, oracle):
         assert got.dtype == np.float32
         np.testing.assert_allclose(got, oracle.lne3d(s / s.max(), fl), rtol=RTOL, atol=5e-7)
     assert hipr_b200.lne3d_fixed(_cuda(torch_cuda, vol), "ME2", 7, 5, 4) is None
+
+
+@pytest.mark.parametrize("flavour", ["ME2", "F2", "F3"])
+def test_neighbor3d_host_entry_point(torch_cuda, oracle, flavour):
+    """hipr_neighbor3d_host: numpy z-stack cube in, numpy score volume out == the device-resident pipeline, bit for
+    bit, and the oracle within the gate."""
+    import hipr_b200
+    from hipr_b200 import synth
+    cube = synth.make_volume_cube(20, 24, 40, 95, seed=3).numpy()
+    got = hipr_b200.neighbor3d_score_host(cube, flavour)
+    dev = hipr_b200.neighbor3d_score(torch_cuda.from_numpy(cube).cuda(), flavour).cpu().numpy()
+    assert np.array_equal(got, dev)
+    s = cube.astype(np.float64).sum(axis=3)
+    want = oracle.lne3d(s / s.max(), flavour)
+    np.testing.assert_allclose(got, want, rtol=1e-5, atol=5e-7)
+    with pytest.raises(ValueError):
+        hipr_b200.neighbor3d_score_host(cube[0], flavour)
