@@ -122,6 +122,14 @@ def test_no_cpu_path():
         hipr_b200.lne2d(torch.zeros(20, 20), "F1")
     with pytest.raises(ValueError, match="no CPU path"):
         hipr_b200.cell_spectra(torch.zeros(4, 4, 3), torch.zeros(4, 4, dtype=torch.int32), 1)
+    for call in (lambda: hipr_b200.register_stacks([torch.zeros(8, 8, 3)]),
+                 lambda: hipr_b200.denoise_nl_means(torch.zeros(40, 40, dtype=torch.float64), h=0.02),
+                 lambda: hipr_b200.cell_geometry(torch.zeros(8, 8, dtype=torch.int32)),
+                 lambda: hipr_b200.paint_labels(torch.zeros(8, 8, dtype=torch.int32), torch.zeros(3)),
+                 lambda: hipr_b200.channel_sum_raw(torch.zeros(8, 8, 3, dtype=torch.uint8), 255.0),
+                 lambda: hipr_b200.neighbor3d_score(torch.zeros(12, 12, 12, 4), "ME2")):
+        with pytest.raises(ValueError, match="no CPU path"):
+            call()
     import neighbor2d
     with pytest.raises(Exception):
         neighbor2d.line_profile_2d_v2(np.zeros((12, 12)), 11, 9)
