@@ -90,8 +90,23 @@ def cpu_single_core(cube_np):
     from oracle import hipr_oracle
     lp, kind = _lp2d()
     t0 = time.perf_counter()
-    hipr_oracle.neighbor2d_score(cube_np, "F1", lp_func=lp)
-    return time.perf_counter() - t0, kind
+    score = hipr_oracle.neighbor2d_score(cube_np, "F1", lp_func=lp)
+    return time.perf_counter() - t0, kind, score
+
+
+def parity_stats(got, want, rtol=1e-5, atol=5e-7):
+    """Deviation of a float32 result from the float64 reference: the counts are what the gates in tests/ assert on
+    windows, here over the whole array."""
+    import numpy as np
+    got = np.asarray(got, dtype=np.float64)
+    want = np.asarray(want, dtype=np.float64)
+    err = np.abs(got - want)
+    nz = want != 0
+    return {"n": int(want.size), "max_abs": float(err.max()), "max_rel": float((err[nz] / np.abs(want[nz])).max()),
+            "n_outside_rtol1e-5_atol0": int((err > rtol * np.abs(want)).sum()),
+            "n_outside_gate": int((err > atol + rtol * np.abs(want)).sum()),
+            "gate": "rtol %g, atol %g (the gate of tests/)" % (rtol, atol),
+            "nan_mismatch": int((np.isnan(got) != np.isnan(want)).sum())}
 
 
 _G = {}
@@ -505,6 +520,7 @@ def run_b200(args):
     torch.cuda.synchronize()
     e2e_wall_ms = 1e3 * (time.perf_counter() - t0)
     score_check = float(score_host.mean())
+    host_api_score = score_host.copy()
     # per-cell spectra end to end: pinned host cube + host label image -> cell table on the host
     labels_host = labels[0].cpu().numpy()
     ops.cell_spectra_host(host, labels_host)
@@ -538,6 +554,14 @@ def run_b200(args):
     ms, cell_ms, e2e_dev_ms, e2e_wall_ms, k1_ms, raw_dev_ms, cell_e2e_ms = [float(x) for x in t.tolist()]
     launches, cells_all = int(cnt[0].item()), float(cnt[1].item())
 
+    # ---- the other configurations, recorded in the same line -----------------------------------
+    # c5 (needs >= 2 ranks): the split mosaic with this library's peer-memory exchange; c4 (1 rank): the z-stack
+    zstack = mosaic = None
+    if not args.no_extras:
+        if world > 1:
+            mosaic = measure_mosaic(args, dev, rank, world, 2048, args.mosaic_side, min(args.steps, 20), hbm_peak=hbm_peak)
+        else:
+            zstack = measure_zstack(args, dev, rank, world, min(args.steps, 10), hbm_peak, with_cpu=not args.no_cpu)
     if rank == 0:
         value = world * npix * args.steps / (ms * 1e-3) / 1e6
         k1_gbs = npix * BYTES_PER_PIXEL / (k1_ms * 1e-3) / 1e9
@@ -550,10 +574,10 @@ def run_b200(args):
             "metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "flavour": "F1", "patch_size": 11, "phi_range": 9, "path": args.path,
-                       "streams": args.streams,
-                       "l2": "inputs larger than L2 (1.59 GB cube per step, %d FOVs in rotation)" % len(cubes),
-                       "arithmetic": "float64 channel sums, 31-bit fixed-point stencil, float32 score"},
+            "config": {"workload": WORKLOAD, "flavour": "F1", "patch_size": 11, "phi_range": 9},
+            "impl_detail": {"path": args.path, "streams": args.streams,
+                            "l2": "inputs larger than L2 (1.59 GB cube per step, %d FOVs in rotation)" % len(cubes),
+                            "arithmetic": "float64 channel sums, 31-bit fixed-point stencil, float32 score"},
             "pipeline_frac_of_hbm_peak": value / world * 1e6 * BYTES_PER_PIXEL / 1e9 / hbm_peak,
             "roofline": {"bound": "hbm", "kernel": "fused2d_kernel" if args.path == "fused" else "chansum_bulk_kernel",
                          "how": "this kernel launched alone K times between two CUDA events, same inputs",
@@ -595,25 +619,125 @@ def run_b200(args):
             crop = cubes[0][:side, :side].cpu().numpy()
             for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
                 os.environ[k] = "1"
-            sec, kind = cpu_single_core(crop)
+            sec, kind, want = cpu_single_core(crop)
+            if side == H:
+                # the oracle just scored the step's whole FOV: compare, do not throw it away
+                from oracle import hipr_oracle
+                dev_score = ops.neighbor2d_pipeline(cubes[0], "F1")[0].cpu().numpy()
+                par = {"score_device": parity_stats(dev_score, want), "score_host_api": parity_stats(host_api_score, want),
+                       "device_equals_host_api_bitwise": bool(np.array_equal(dev_score, host_api_score)),
+                       "reference": "oracle/_ref line_profile_2d_v2 + the scripts' numpy blocks in float64, whole 2048^2 FOV"
+                                    if kind == "reference" else "oracle port, whole FOV"}
+                wl, wa, wavg, wnorm = hipr_oracle.cell_spectra(labels_host, crop)
+                gl, ga, gavg, gnorm = cell_tab
+                same = bool(np.array_equal(gl, wl) and np.array_equal(ga, wa))
+                par["cell_spectra"] = {"labels_and_areas_equal": same, "n_cells": int(wl.size),
+                                       "max_rel_mean": float(np.max(np.abs(gavg - wavg) / np.abs(wavg))) if same else None,
+                                       "max_rel_norm": float(np.max(np.abs(gnorm - wnorm) / np.maximum(np.abs(wnorm), 1e-300))) if same else None,
+                                       "gate": "labels / pixel counts bit-exact, means rtol 1e-5"}
+                line["parity"] = par
             line["cpu_baseline"] = {"value": side * side / sec / 1e6, "unit": "Mpix/s", "cores": 1, "kind": kind,
                                     "sample": "%dx%dx%d crop of the step's FOV, single process (the reference is "
                                               "single-threaded), %.1f s" % (side, side, C, sec),
                                     "host_cores_available": len(os.sched_getaffinity(0))}
+        if zstack is not None:
+            line["zstack"] = zstack
+        if mosaic is not None:
+            line["mosaic"] = mosaic
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
-def run_mosaic(args):
-    """BASELINE config 5: a stitched side x side x 95 mosaic cut into row slabs, one per rank.  Per step:
-    channel sum of the slab -> 5-row halo exchange of the sum image + reduction of its max/min (--exchange p2p:
-    this library's kernels over NVLink peer memory; nccl: send/recv + all-reduce) -> fixed-point stencil on the
-    extended slab; then per-cell spectra with an all-reduce of the
-    (L+1, C) partial sums and integer counts.  Extra line, not the headline metric."""
+def measure_mosaic(args, dev, rank, world, rows, width, steps, exchanges=("p2p", "p2p_inorder", "nccl"), hbm_peak=6554.2):
+    """BASELINE config 5 on the ranks of an initialised NCCL job: a stitched (rows * world) x width x 95 mosaic cut into
+    row slabs, one per rank.  Per step: channel sum of the slab -> 5-row halo exchange of the sum image (+ max / min) ->
+    fixed-point stencil on the extended slab; then per-cell spectra reduced to rank 0.  Exchange kinds:
+      p2p          this library's push / wait kernels over NVLink peer memory, row-banded so that stencil and exchange
+                   run under the channel sum (hipr_mosaic_p2p_score);
+      p2p_inorder  the same kernels, sum -> exchange -> stencil in order (bit-identical to nccl);
+      nccl         batch_isend_irecv + all_reduce.
+    Returns the dict on rank 0 (None elsewhere)."""
     import torch
     import torch.distributed as dist
-    from hipr_b200 import ops, sharding, synth
+    from hipr_b200 import sharding, synth
+
+    height = rows * world
+    r0 = rank * rows
+    labels_full, L = synth.make_labels(height, width, seed=4321, device=dev)
+    labels = labels_full[r0:r0 + rows].contiguous()
+    del labels_full
+    cube = torch.empty((rows, width, C), dtype=torch.float32, device=dev)
+    for a in range(0, rows, 256):        # generated in 256-row pieces to bound peak memory
+        b = min(a + 256, rows)
+        cube[a:b] = synth.make_cube(b - a, width, C, seed=1234 + r0 + a, device=dev, labels=labels[a:b])
+    slab = sharding.MosaicSlab()
+    p2p = sharding.P2PMosaicSlab(rows, width)
+    bands = args.bands if args.bands else 16     # 16 k wide slabs: 8 bands -> 2.31 ms, 16 -> 2.23 ms (round 1)
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    runners = {"p2p": lambda: p2p.score(cube, "F1", bands=bands), "p2p_inorder": lambda: p2p.score(cube, "F1"),
+               "nccl": lambda: slab.score(cube, "F1")}
+    out = {}
+    for kind in exchanges:
+        run = runners[kind]
+        for _ in range(3):
+            score = run()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            score = run()
+        e1.record()
+        barrier()
+        p2p.check_peers()
+        t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        chk = score.double().sum().reshape(1)
+        nan = torch.isnan(score).sum().reshape(1).double()
+        dist.all_reduce(chk)
+        dist.all_reduce(nan)
+        out[kind] = {"ms_per_step": float(t.item()), "score_checksum": float(chk.item()), "nan_pixels": int(nan.item())}
+    for _ in range(2):
+        slab.cell_spectra(cube, labels, L, root=0)
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    c0.record()
+    for _ in range(steps):
+        cells = slab.cell_spectra(cube, labels, L, root=0)      # one table, on rank 0 (reduce, not all-reduce)
+    c1.record()
+    barrier()
+    t = torch.tensor([c0.elapsed_time(c1) / steps], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    cms = float(t.item())
+    p2p.close()
+    del cube, labels
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    npix = height * width
+    best = exchanges[0]
+    ms = out[best]["ms_per_step"]
+    res = {"workload": "c5: %dx%dx%d mosaic, %d row slabs of %d rows (the 16384^2 mosaic at 8 GPUs; the same slab per GPU "
+                       "at smaller N)" % (height, width, C, world, rows),
+           "flavour": "F1", "steps": steps, "exchange": best, "row_bands": bands,
+           "ms_per_step": ms, "mpix_per_s": npix / (ms * 1e-3) / 1e6,
+           "frac_of_hbm_peak_per_gpu": rows * width * BYTES_PER_PIXEL / (ms * 1e-3) / 1e9 / hbm_peak,
+           "halo_bytes_per_neighbour": 5 * width * 8, "by_exchange": out,
+           "cell_spectra": {"cells": int(cells[0].numel()), "ms_per_step": cms, "cells_per_s": int(cells[0].numel()) / (cms * 1e-3),
+                            "reduce_to_rank0_bytes": (L + 1) * (C * 8 + 4)}}
+    if "p2p_inorder" in out and "nccl" in out:
+        res["checksum_equal_p2p_inorder_nccl"] = out["p2p_inorder"]["score_checksum"] == out["nccl"]["score_checksum"]
+    return res
+
+
+def run_mosaic(args):
+    """--workload mosaic: config 5 alone (extra line, not the headline metric)."""
+    import torch
+    import torch.distributed as dist
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -624,86 +748,26 @@ def run_mosaic(args):
         raise SystemExit("--workload mosaic needs torchrun with >= 2 ranks")
     dist.init_process_group("nccl", device_id=dev)
     side = args.mosaic_side
-    r0, r1 = sharding.slab_bounds(side, rank, world)
-    rows = r1 - r0
-    # slab of the synthetic mosaic, generated in 256-row pieces to bound peak memory
-    labels_full_rows, L = synth.make_labels(side, side, seed=4321, device=dev)
-    labels = labels_full_rows[r0:r1].contiguous()
-    del labels_full_rows
-    cube = torch.empty((rows, side, C), dtype=torch.float32, device=dev)
-    for a in range(0, rows, 256):
-        b = min(a + 256, rows)
-        cube[a:b] = synth.make_cube(b - a, side, C, seed=1234 + r0 + a, device=dev, labels=labels[a:b])
-    slab = sharding.MosaicSlab()
-    scorer = sharding.P2PMosaicSlab(rows, side) if args.exchange == "p2p" else slab
-
-    def barrier():
-        dist.barrier()
-        torch.cuda.synchronize()
-
-    kw = {"bands": args.bands if args.bands else 16} if args.exchange == "p2p" else {}   # 16 k wide slabs: 8 -> 2.31 ms, 16 -> 2.23 ms
-    for _ in range(max(args.warmup, 3)):
-        scorer.score(cube, "F1", **kw)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        score = scorer.score(cube, "F1", **kw)
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    for _ in range(2):
-        slab.cell_spectra(cube, labels, L, root=0)
-    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    c0.record()
-    for _ in range(args.steps):
-        cells = slab.cell_spectra(cube, labels, L, root=0)      # one table, on rank 0 (reduce, not all-reduce)
-    c1.record()
-    barrier()
-    cms = c0.elapsed_time(c1)
-    t = torch.tensor([ms, cms], dtype=torch.float64, device=dev)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, cms = [float(x) for x in t.tolist()]
+    kinds = ("p2p", "p2p_inorder", "nccl") if args.exchange == "p2p" else ("nccl",)
+    res = measure_mosaic(args, dev, rank, world, side // world, side, args.steps, kinds)
     if rank == 0:
-        npix = side * side
-        print(json.dumps({
-            "metric": "mosaic neighbor2d Mpix/s (row slabs + 5-row halo exchange over NVLink)", "value": npix * args.steps / (ms * 1e-3) / 1e6,
-            "unit": "Mpix/s", "n_gpus": world, "steps": args.steps, "ms_per_step": ms / args.steps, "scaling": "strong",
-            "config": {"workload": "c5: %dx%dx%d mosaic, %d row slabs of %d rows" % (side, side, C, world, rows),
-                       "halo_bytes_per_neighbour": 5 * side * 8, "flavour": "F1",
-                       "exchange": "own kernels over NVLink peer memory (csrc/mosaic_p2p.cu), %d row bands: stencil and exchange "
-                                   "under the channel sum" % kw["bands"] if args.exchange == "p2p"
-                       else "NCCL send/recv + all-reduce"},
-            "frac_of_hbm_peak_per_gpu": npix / world * BYTES_PER_PIXEL / (ms / args.steps * 1e-3) / 1e9 / 6554.2,
-            "cell_spectra": {"cells": int(cells[0].numel()), "ms_per_step": cms / args.steps,
-                             "cells_per_s": int(cells[0].numel()) * args.steps / (cms * 1e-3),
-                             "reduce_to_rank0_bytes": (L + 1) * (C * 8 + 4)},
-            "score_mean_rank0": float(score.mean())}), flush=True)
-    if args.exchange == "p2p":
-        scorer.check_peers()
-        scorer.close()
+        print(json.dumps({"metric": "mosaic neighbor2d Mpix/s (row slabs + 5-row halo exchange over NVLink)",
+                          "value": res["mpix_per_s"], "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
+                          "ms_per_step": res["ms_per_step"], "scaling": "strong", "config": {"workload": res["workload"]},
+                          "mosaic": res}), flush=True)
     dist.destroy_process_group()
 
 
-def run_zstack(args):
+def measure_zstack(args, dev, rank, world, steps, hbm_peak, with_cpu=True):
     """BASELINE config 4: one X x Y x Z x 95 z-stack through the 72-direction 3-D stencil, the
     `generate_3d_segmentation_memory_efficient` chain (bio/..._analysis.py:807-817): channel sum -> /max ->
-    edge pad -> line_profile_memory_efficient_v2 -> mean * (1 - qcv) over the 72 directions.  Extra line, not
-    the headline metric.  With N ranks every rank has its own z-stack (independent volumes, no collective)."""
+    edge pad -> line_profile_memory_efficient_v2 -> mean * (1 - qcv) over the 72 directions.  With N ranks every
+    rank has its own z-stack (independent volumes, no collective).  Returns the dict on rank 0."""
     import numpy as np
     import torch
     import torch.distributed as dist
     import hipr_b200
     from hipr_b200 import ops, synth
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
         if world > 1:
@@ -726,66 +790,100 @@ def run_zstack(args):
     def k1():
         return ops.channel_sum(cube, None, normalize=False, dtype=torch.float64, return_max=True)
 
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(3):
         score = step()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     l0 = lib.hipr_launch_count()
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         score = step()
     e1.record()
     barrier()
     launches = lib.hipr_launch_count() - l0
-    ms = e0.elapsed_time(e1) / args.steps
+    ms = e0.elapsed_time(e1) / steps
     r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    k1()
+    s64, mk = k1()
     barrier()
     r0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         k1()
     r1.record()
     barrier()
-    k1_ms = r0.elapsed_time(r1) / args.steps
-    t = torch.tensor([ms, k1_ms], dtype=torch.float64, device=dev)
+    k1_ms = r0.elapsed_time(r1) / steps
+    # the stencil alone, on the resident sum volume
+    ops.lne3d_fixed(s64, "ME2", maxkey=mk)
+    q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    q0.record()
+    for _ in range(steps):
+        ops.lne3d_fixed(s64, "ME2", maxkey=mk)
+    q1.record()
+    barrier()
+    k4_ms = q0.elapsed_time(q1) / steps
+    t = torch.tensor([ms, k1_ms, k4_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, k1_ms = [float(v) for v in t.tolist()]
+    ms, k1_ms, k4_ms = [float(v) for v in t.tolist()]
+    res = None
     if rank == 0:
-        hbm_peak = 6554.2
-        try:
-            hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
-        except Exception:
-            pass
-        line = {"metric": "neighbor (3-D) Mvox/s at %dx%dx%dx95ch" % (X, Y, Z), "value": world * nvox / (ms * 1e-3) / 1e6,
-                "unit": "Mvox/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
-                "higher_is_better": True, "scaling": "weak", "dtype": "f32", "data": "synthetic",
-                "config": {"workload": "c4: %dx%dx%dx95 float32 z-stack per GPU, (11, 9, 9) stencil, epilogue ME2" % (X, Y, Z),
-                           "arithmetic": "float64 channel sums, 31-bit fixed-point stencil, float32 score",
-                           "l2": "inputs larger than L2 (%.1f GB cube per step)" % (nvox * C * 4 / 1e9)},
-                "pipeline_frac_of_hbm_peak": nvox * BYTES_PER_PIXEL / (ms * 1e-3) / 1e9 / hbm_peak,
-                "roofline": {"bound": "hbm", "kernel": "chansum_bulk_kernel", "achieved": nvox * BYTES_PER_PIXEL / (k1_ms * 1e-3) / 1e9,
-                             "peak": hbm_peak, "unit": "GB/s", "frac": nvox * BYTES_PER_PIXEL / (k1_ms * 1e-3) / 1e9 / hbm_peak,
-                             "ms_per_launch": k1_ms, "traffic": None},
-                "stencil_ms": ms - k1_ms, "stencil_note": "lne3d_q_kernel is bound by shared-memory loads + FMNMX, not HBM",
-                "gpu_launches": launches, "score_mean": float(score.mean())}
-        if not args.no_cpu and world == 1:
-            # the reference's own 3-D chain on a 32^3 sub-volume (it runs at a few thousand voxels per second)
+        res = {"metric": "neighbor (3-D) Mvox/s at %dx%dx%dx95ch" % (X, Y, Z), "value": world * nvox / (ms * 1e-3) / 1e6,
+               "unit": "Mvox/s", "n_gpus": world, "steps": steps, "warmup": 3, "ms_per_step": ms,
+               "higher_is_better": True, "scaling": "weak", "dtype": "f32", "data": "synthetic",
+               "config": {"workload": "c4: %dx%dx%dx95 float32 z-stack per GPU, (11, 9, 9) stencil, epilogue ME2" % (X, Y, Z)},
+               "impl_detail": {"arithmetic": "float64 channel sums, 31-bit fixed-point stencil, float32 score",
+                               "l2": "inputs larger than L2 (%.1f GB cube per step)" % (nvox * C * 4 / 1e9)},
+               "pipeline_frac_of_hbm_peak": nvox * BYTES_PER_PIXEL / (ms * 1e-3) / 1e9 / hbm_peak,
+               "roofline": {"bound": "hbm", "kernel": "chansum_bulk_kernel", "achieved": nvox * BYTES_PER_PIXEL / (k1_ms * 1e-3) / 1e9,
+                            "peak": hbm_peak, "unit": "GB/s", "frac": nvox * BYTES_PER_PIXEL / (k1_ms * 1e-3) / 1e9 / hbm_peak,
+                            "ms_per_launch": k1_ms, "traffic": None},
+               "stencil": {"kernel": "lne3d_q_kernel", "ms_per_launch": k4_ms, "mvox_per_s": nvox / (k4_ms * 1e-3) / 1e6,
+                           "bound": "ALU pipe (min / max issue), not HBM: 12 B per voxel"},
+               "gpu_launches": launches, "score_mean": float(score.mean())}
+        if with_cpu and world == 1:
+            # the reference's own 3-D chain on a 32^3 sub-volume (it runs at a few thousand voxels per second), and the
+            # same sub-volume through the CUDA path: parity on what the CPU can finish
             from oracle import hipr_oracle, load_ref
             ref = load_ref("neighbor")
             me2 = ref.line_profile_memory_efficient_v2 if ref is not None else hipr_oracle.line_profile_memory_efficient_v2
             n = 32
-            sub = cube[:n, :n, :n].cpu().numpy()
+            sub = cube[:n, :n, :n].contiguous()
+            sub_np = sub.cpu().numpy()
             t0 = time.perf_counter()
-            sm = np.sum(sub, axis=3)
+            sm = np.sum(sub_np, axis=3)
             sm = sm / np.max(sm)
             dirs = np.asarray(me2(np.pad(sm, 5, mode="edge").astype(np.float64), 11, 9, 9))
-            hipr_oracle.epilogue_F2_dirs(dirs)
+            want = hipr_oracle.epilogue_F2_dirs(dirs)
             sec = time.perf_counter() - t0
-            line["cpu_baseline"] = {"value": n ** 3 / sec / 1e6, "unit": "Mvox/s", "cores": 1,
-                                    "kind": "reference" if ref is not None else "port",
-                                    "sample": "%d^3 sub-volume through line_profile_memory_efficient_v2 + numpy epilogue, %.1f s" % (n, sec)}
-        print(json.dumps(line), flush=True)
+            res["cpu_baseline"] = {"value": n ** 3 / sec / 1e6, "unit": "Mvox/s", "cores": 1,
+                                   "kind": "reference" if ref is not None else "port",
+                                   "sample": "%d^3 sub-volume through line_profile_memory_efficient_v2 + numpy epilogue, %.1f s" % (n, sec)}
+            res["parity"] = parity_stats(ops.neighbor3d_score(sub, "ME2").cpu().numpy(), want)
+    del cube
+    torch.cuda.empty_cache()
+    return res
+
+
+def run_zstack(args):
+    """--workload zstack: config 4 alone (extra line, not the headline metric)."""
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    hbm_peak = 6554.2
+    try:
+        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        pass
+    res = measure_zstack(args, dev, rank, world, args.steps, hbm_peak, with_cpu=not args.no_cpu)
+    if rank == 0:
+        print(json.dumps(res), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

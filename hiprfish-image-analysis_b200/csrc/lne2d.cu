@@ -124,9 +124,12 @@ template <typename T>
 __global__ void __launch_bounds__(GA_THREADS)
 gather_kernel(const T *__restrict__ src, int64_t stride_a, int64_t stride_b, int inner,
               int64_t nrows /*output rows = a * inner + b*/, int rowlen /*output pixels per row*/,
-              int chunk /*pixels per CTA*/, int K, const int *__restrict__ offs_dev, T *__restrict__ out) {
+              int chunk /*pixels per CTA*/, int K, const __grid_constant__ Table2D offs /*K linear offsets*/,
+              T *__restrict__ out) {
+    // the table travels in the kernel parameter bank (<= 3840 B): no device copy to keep coherent with the launch
+    // stream or the current device; staged in shared memory because it is indexed by a runtime k
     extern __shared__ int s_off[];
-    for (int i = threadIdx.x; i < K; i += GA_THREADS) s_off[i] = offs_dev[i];
+    for (int i = threadIdx.x; i < K; i += GA_THREADS) s_off[i] = offs.off[i];
     __syncthreads();
     const int chunks_per_row = (rowlen + chunk - 1) / chunk;
     constexpr int VEC = 16 / sizeof(T);
@@ -162,34 +165,6 @@ gather_kernel(const T *__restrict__ src, int64_t stride_a, int64_t stride_b, int
             obase[e] = sbase[p + s_off[k]];
         }
     }
-}
-
-// cached device copies of literal-gather offset tables (tiny; keyed by content)
-struct OffCache {
-    int *dev = nullptr;
-    int n = 0;
-    int host[HIPR_MAX_TABLE];
-};
-static OffCache g_offcache[8];
-static int g_offcache_next = 0;
-
-int upload_offsets(const int *lin, int n, cudaStream_t st, const int **dev_out) {
-    for (auto &c : g_offcache)
-        if (c.dev && c.n == n && memcmp(c.host, lin, n * sizeof(int)) == 0) {
-            *dev_out = c.dev;
-            return HIPR_OK;
-        }
-    OffCache &c = g_offcache[g_offcache_next];
-    g_offcache_next = (g_offcache_next + 1) % 8;
-    if (!c.dev) HIPR_CUDA(cudaMalloc(&c.dev, HIPR_MAX_TABLE * sizeof(int)));
-    // synchronous w.r.t. the host buffer; ordered before later work on any stream by the
-    // blocking copy semantics of pageable memory
-    HIPR_CUDA(cudaMemcpy(c.dev, lin, n * sizeof(int), cudaMemcpyHostToDevice));
-    memcpy(c.host, lin, n * sizeof(int));
-    c.n = n;
-    (void)st;
-    *dev_out = c.dev;
-    return HIPR_OK;
 }
 
 int check_table(const int32_t *table, int n_dirs, int P, int ndim) {
@@ -242,16 +217,16 @@ static int lne2d_dispatch(const T *img, int Hs, int Ws, int64_t ld, int padded, 
 template <typename T>
 int gather_launch(const T *src, int64_t stride_a, int64_t stride_b, int inner, int64_t nrows, int rowlen,
                   int K, const int *lin, T *out, cudaStream_t st) {
-    const int *offs_dev = nullptr;
-    int e = upload_offsets(lin, K, st, &offs_dev);
-    if (e) return e;
+    if (K < 1 || K > HIPR_MAX_TABLE) return HIPR_E_TABLE;
+    Table2D offs;
+    memcpy(offs.off, lin, K * sizeof(int));
     int chunk = 128;
     if (K > 256) chunk = 16;   // 3-D: 792 values per voxel
     const int64_t work = nrows * ((rowlen + chunk - 1) / chunk);
     int64_t grid = (int64_t)sm_count() * 8;
     if (grid > work) grid = work;
     gather_kernel<T><<<(unsigned)grid, GA_THREADS, K * sizeof(int), st>>>(src, stride_a, stride_b, inner, nrows, rowlen,
-                                                                         chunk, K, offs_dev, out);
+                                                                         chunk, K, offs, out);
     return after_launch();
 }
 template int gather_launch<float>(const float *, int64_t, int64_t, int, int64_t, int, int, const int *, float *,

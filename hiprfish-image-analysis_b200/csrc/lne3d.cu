@@ -21,6 +21,11 @@ int check_table(const int32_t *table, int n_dirs, int P, int ndim);
 struct Table3D {
     int off[HIPR_MAX_TABLE];
 };
+// the generic kernel's (t, li, 3) table, by value in the kernel parameter bank (11.5 KB; the limit is 32 KB since
+// CUDA 12.1): no device copy to keep coherent with streams, devices or threads
+struct Table3DFull {
+    int v[HIPR_MAX_TABLE * 3];
+};
 
 constexpr int L3_P = 11, L3_T = 72, L3_HALF = 5;
 constexpr int L3_TY = 8, L3_TZ = 32;
@@ -241,7 +246,7 @@ lne3d_q_kernel(const SrcT *__restrict__ vol, int Xs, int Ys, int Zs, int src_off
 template <typename T>
 __global__ void __launch_bounds__(128)
 lne3d_generic_kernel(const T *__restrict__ vol, int Xs, int Ys, int Zs, int src_off, int X, int Y, int Z,
-                     int P, int Tn, const int *__restrict__ tab /* (t, li, 3) device */, int flavour, int mode,
+                     int P, int Tn, const __grid_constant__ Table3DFull tabp /* (t, li, 3) */, int flavour, int mode,
                      int flat, const unsigned long long *__restrict__ maxkey, T *__restrict__ out) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (int64_t)X * Y * Z) return;
@@ -258,7 +263,7 @@ lne3d_generic_kernel(const T *__restrict__ vol, int Xs, int Ys, int Zs, int src_
         T mn = (T)0, mx = (T)0, centre = (T)0;
         bool bad = false;
         for (int li = 0; li < P; ++li) {
-            const int *o = tab + (t * P + li) * 3;
+            const int *o = tabp.v + (t * P + li) * 3;
             T s;
             if (flat) {
                 const int64_t a = ((int64_t)(x + o[0]) * Ys + (y + o[1])) * Zs + (z + o[2]);
@@ -289,8 +294,6 @@ lne3d_generic_kernel(const T *__restrict__ vol, int Xs, int Ys, int Zs, int src_
         out[idx] = reduce_dirs_runtime<T>(r, Tn, flavour);
     }
 }
-
-int upload_offsets(const int *lin, int n, cudaStream_t st, const int **dev_out);
 
 template <typename T, int FLAVOUR, int MODE, bool BAKED>
 static int launch_fast3d_b(const T *vol, int Xs, int Ys, int Zs, int src_off, int X, int Y, int Z, const Table3D &tab,
@@ -348,22 +351,13 @@ static int lne3d_dispatch(const T *vol, int Xs, int Ys, int Zs, int padded, int 
     if (flavour != HIPR_FLAVOUR_F2 && flavour != HIPR_FLAVOUR_F3 && flavour != HIPR_FLAVOUR_ME2 && !flat)
         return HIPR_E_FLAVOUR;
     if (Tn * P * 3 > HIPR_MAX_TABLE * 3) return HIPR_E_TABLE;
-    // the generic kernel reads the (t, li, 3) table from global memory; cache it like K2's offsets
-    static int *tab_dev = nullptr;
-    static int tab_host[HIPR_MAX_TABLE * 3];
-    static int tab_n = 0;
-    const int n = Tn * P * 3;
-    if (!tab_dev) HIPR_CUDA(cudaMalloc(&tab_dev, sizeof(tab_host)));
-    if (tab_n != n || memcmp(tab_host, table, n * sizeof(int)) != 0) {
-        HIPR_CUDA(cudaDeviceSynchronize());  // a previous launch may still read the old table
-        HIPR_CUDA(cudaMemcpy(tab_dev, table, n * sizeof(int), cudaMemcpyHostToDevice));
-        memcpy(tab_host, table, n * sizeof(int));
-        tab_n = n;
-    }
+    static_assert(sizeof(Table3DFull) <= 32000, "kernel parameter bank");
+    Table3DFull tabp;
+    memcpy(tabp.v, table, (size_t)Tn * P * 3 * sizeof(int));
     const int64_t nv = (int64_t)X * Y * Z;
     if ((nv + 127) / 128 > 0x7fffffffLL) return HIPR_E_RANGE;
     lne3d_generic_kernel<T><<<(unsigned)((nv + 127) / 128), 128, 0, st>>>(vol, Xs, Ys, Zs, src_off, X, Y, Z, P, Tn,
-                                                                         tab_dev, flavour, mode, flat ? 1 : 0,
+                                                                         tabp, flavour, mode, flat ? 1 : 0,
                                                                          maxkey, out);
     return after_launch();
 }

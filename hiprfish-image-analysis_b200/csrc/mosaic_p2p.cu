@@ -57,6 +57,9 @@ static int mosaic_side(MosaicSide **out) {
 }
 constexpr int MP_MAX_WORLD = 64;
 
+// how long a wait kernel spins for its peers before it gives up (SM clocks; hipr_mosaic_p2p_set_timeout_ms)
+static std::atomic<long long> g_wait_timeout_clocks{20ll * 1000 * 1000 * 1000};   // ~10 s at 1.97 GHz
+
 struct MosaicLayout {
     int64_t ext_elems;     // doubles per parity
     int64_t keys_off;      // byte offsets from the base
@@ -146,9 +149,35 @@ mosaic_wait_kernel(unsigned char *base, int world, int rows_max, int W, int pari
     }
 }
 
+// A wait kernel that timed out set *error: the stencil that followed read stale halo rows (and, for F3, a stale
+// range), so the score of this call is poisoned with NaN.  The failure is then visible in the data itself, without a
+// host synchronisation, even if the caller never polls the flag.  One CTA reads the flag; nothing else happens when
+// it is clear.
+__global__ void __launch_bounds__(256)
+mosaic_guard_kernel(const int *__restrict__ error, float *__restrict__ score, int64_t n) {
+    if (*error == 0) return;
+    const float nan = __int_as_float(0x7fc00000);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) score[i] = nan;
+}
+
 }  // namespace hipr
 
 using namespace hipr;
+
+extern "C" int hipr_mosaic_p2p_set_timeout_ms(double ms) {
+    if (!(ms > 0.0) || ms > 3.6e6) return HIPR_E_ARG;
+    int dev = 0, khz = 0;
+    HIPR_CUDA(cudaGetDevice(&dev));
+    if (cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev) != cudaSuccess || khz <= 0) khz = 1965000;
+    g_wait_timeout_clocks.store((long long)(ms * (double)khz));
+    return HIPR_OK;
+}
+
+extern "C" int hipr_mosaic_p2p_guard(const int32_t *error_dev, float *score_dev, int64_t n, void *stream) {
+    if (!error_dev || !score_dev || n < 1) return HIPR_E_ARG;
+    mosaic_guard_kernel<<<148, 256, 0, (cudaStream_t)stream>>>(error_dev, score_dev, n);
+    return after_launch();
+}
 
 extern "C" int64_t hipr_mosaic_p2p_bytes(int rows_max, int W, int world) {
     if (rows_max < MP_HALO || W < 1 || world < 1 || world > MP_MAX_WORLD) return HIPR_E_ARG;
@@ -211,7 +240,7 @@ extern "C" int hipr_mosaic_p2p_exchange(void *const *bases_host, int rank, int w
                                            (unsigned long long)epoch);
     int e = after_launch();
     if (e) return e;
-    const long long timeout = 20ll * 1000 * 1000 * 1000;   // ~10 s of SM clocks
+    const long long timeout = g_wait_timeout_clocks.load();
     mosaic_wait_kernel<<<1, MP_MAX_WORLD, 0, st>>>(pb.base[rank], world, rows_max, W, parity, (unsigned long long)epoch,
                                                    timeout, reinterpret_cast<unsigned long long *>(range_out_dev), error_dev);
     return after_launch();
@@ -253,7 +282,9 @@ extern "C" int hipr_mosaic_p2p_score(const float *cube_slab_dev, int C, void *co
         if ((e = hipr_mosaic_p2p_exchange(bases_host, rank, world, rows, rows_up, rows_max, W, parity, keys_local_dev, epoch,
                                           range_dev, error_dev, stream)))
             return e;
-        return lne2d_q_rows(img, Hs, W, W, 0, HIPR_F64, table_host, flavour, range_dev, out_ext, n_top, n_top + rows, st);
+        if ((e = lne2d_q_rows(img, Hs, W, W, 0, HIPR_F64, table_host, flavour, range_dev, out_ext, n_top, n_top + rows, st)))
+            return e;
+        return hipr_mosaic_p2p_guard(error_dev, score_dev, (int64_t)rows * W, stream);
     }
     std::lock_guard<std::mutex> lock(g_mside_mu);
     MosaicSide *sd = nullptr;
@@ -296,12 +327,12 @@ extern "C" int hipr_mosaic_p2p_score(const float *cube_slab_dev, int C, void *co
     // the two edge bands need the neighbours' rows
     HIPR_CUDA(cudaStreamWaitEvent(sd->s, sd->pushed, 0));
     mosaic_wait_kernel<<<1, MP_MAX_WORLD, 0, sd->s>>>(pb.base[rank], world, rows_max, W, parity, (unsigned long long)epoch,
-                                                      20ll * 1000 * 1000 * 1000,
+                                                      g_wait_timeout_clocks.load(),
                                                       reinterpret_cast<unsigned long long *>(range_dev), error_dev);
     if ((e = after_launch())) return e;
     if ((e = stencil(0))) return e;
     if ((e = stencil(nb - 1))) return e;
     HIPR_CUDA(cudaEventRecord(sd->done, sd->s));
     HIPR_CUDA(cudaStreamWaitEvent(st, sd->done, 0));
-    return HIPR_OK;
+    return hipr_mosaic_p2p_guard(error_dev, score_dev, (int64_t)rows * W, stream);
 }

@@ -49,6 +49,8 @@ _SIGNATURES = {
     "hipr_p2p_close_handle": (_i, [_vp]),
     "hipr_mosaic_p2p_rows_ptr": (_i, [_vp, _i, _i, _i, _i, _i, C.POINTER(_vp)]),
     "hipr_mosaic_p2p_exchange": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, C.c_uint64, _vp, _vp, _vp]),
+    "hipr_mosaic_p2p_set_timeout_ms": (_i, [C.c_double]),
+    "hipr_mosaic_p2p_guard": (_i, [_vp, _vp, _i64, _vp]),
     "hipr_mosaic_p2p_score": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, C.c_uint64, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "hipr_neighbor2d_host": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp]),
     "hipr_neighbor3d_host": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),

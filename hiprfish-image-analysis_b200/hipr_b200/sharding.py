@@ -118,9 +118,17 @@ class P2PMosaicSlab:
     rank's table and releases a flag, one wait kernel acquires the flags and reduces the range.  torch.distributed
     is used once, at construction, to exchange the 64-byte IPC handles and the slab heights.
 
-    One instance per (slab height, width); every rank must call score() the same number of times."""
+    One instance per (slab height, width); every rank must call score() the same number of times.
 
-    def __init__(self, rows, width, group=None):
+    Failure handling: if a peer does not deliver within `timeout_ms` (default ~10 s; a rank still loading its slab
+    can be late by more: raise it), the wait kernel gives up instead of hanging the GPU and that call's score is
+    overwritten with NaN on the device (hipr_mosaic_p2p_guard), so a stale halo never passes as a result;
+    score(check=True) or check_peers() synchronises and raises instead.
+
+    group: the process group used for the one-time handle exchange; a gloo group works (the data path never touches
+    torch.distributed), which also lets two ranks share one GPU (cudaIpc mappings work within a device)."""
+
+    def __init__(self, rows, width, group=None, timeout_ms=None):
         import ctypes as C
         from ._lib import check, lib
         self._C, self._check, self._lib = C, check, lib()
@@ -135,6 +143,8 @@ class P2PMosaicSlab:
         nbytes = self._lib.hipr_mosaic_p2p_bytes(self.rows_max, self.width, self.world)
         if nbytes <= 0:
             raise ValueError("mosaic geometry not supported by the peer-memory exchange")
+        if timeout_ms is not None:
+            check(self._lib.hipr_mosaic_p2p_set_timeout_ms(float(timeout_ms)), "p2p_set_timeout_ms")
         base = C.c_void_p()
         check(self._lib.hipr_p2p_alloc(C.byref(base), nbytes), "p2p_alloc")
         self._own = base
@@ -168,8 +178,9 @@ class P2PMosaicSlab:
                                                        int(with_top_halo), C.byref(p)), "p2p_rows_ptr")
         return p
 
-    def score(self, cube_slab, flavour="F1", bands=0):
-        """bands >= 3 (F1 / F2): one call that also hides the stencil under the channel sum, band by band
+    def score(self, cube_slab, flavour="F1", bands=0, check=False):
+        """check=True: synchronise and raise if a peer timed out (otherwise a timed-out call returns NaN scores).
+        bands >= 3 (F1 / F2): one call that also hides the stencil under the channel sum, band by band
         (hipr_mosaic_p2p_score; every tile quantised with its own range).  bands = 0: channel sum, exchange,
         stencil in order (bit-identical to MosaicSlab.score); F3 uses the exchanged global range."""
         from . import tables
@@ -193,6 +204,8 @@ class P2PMosaicSlab:
                                                         int(bands), keys, C.c_void_p(self._range.data_ptr()),
                                                         C.c_void_p(self._error.data_ptr()), C.c_void_p(out.data_ptr()), st),
                         "mosaic_p2p_score")
+            if check:
+                self.check_peers()
             return out
         # channel sums straight into this rank's peer-mapped buffer (rows 5 .. 5 + rows of ext[parity])
         self._check(self._lib.hipr_chansum(C.c_void_p(cube_slab.data_ptr()), None, self.rows * self.width, Cn,
@@ -211,6 +224,10 @@ class P2PMosaicSlab:
                                            tab.ctypes.data_as(C.c_void_p), FLAVOURS[flavour],
                                            C.c_void_p(self._range.data_ptr()) if flavour not in ("F1", "F2") else None,
                                            C.c_void_p(out.data_ptr()), st), "lne2d_q")
+        self._check(self._lib.hipr_mosaic_p2p_guard(C.c_void_p(self._error.data_ptr()), C.c_void_p(out.data_ptr()),
+                                                    out.numel(), st), "mosaic_p2p_guard")
+        if check:
+            self.check_peers()
         return out[n_top: Hs - n_bottom]
 
     def check_peers(self):

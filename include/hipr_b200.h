@@ -311,6 +311,13 @@ int hipr_mosaic_p2p_exchange(void *const *bases_host, int rank, int world, int r
                              int W, int parity, const uint64_t *keys_local_dev, uint64_t epoch,
                              uint64_t *range_out_dev, int32_t *error_dev, void *stream);
 
+/* Failure handling.  A wait kernel that does not see every peer's flag within the timeout (default ~10 s of SM
+ * clocks; hipr_mosaic_p2p_set_timeout_ms changes it process-wide) sets *error_dev = 1 instead of hanging the GPU.
+ * hipr_mosaic_p2p_guard, enqueued after the stencil, then overwrites that call's score with NaN, so a stale halo can
+ * never pass as a result even if the caller does not poll error_dev (hipr_mosaic_p2p_score calls it itself). */
+int hipr_mosaic_p2p_set_timeout_ms(double ms);
+int hipr_mosaic_p2p_guard(const int32_t *error_dev, float *score_dev, int64_t n, void *stream);
+
 /* The whole slab in one call, cube_slab_dev (rows, W, C) float32 -> score_dev (rows, W) float32, with the exchange
  * and the stencil hidden under the channel sum: row bands, first and last band summed first and their edge rows
  * pushed, then the channel sum of band b + 1 on `stream` while the stencil of band b runs on an internal side

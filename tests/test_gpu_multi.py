@@ -125,3 +125,86 @@ def test_mosaic_two_gpus_peer_memory(torch_cuda, tmp_path):
         pytest.skip("needs 2 GPUs")
     _spawn(_p2p_worker, tmp_path, 29800 + (os.getpid() % 1000))
     assert all((tmp_path / ("p2p%d" % r)).exists() for r in range(2))
+
+
+# ---- the same peer-memory exchange with BOTH ranks on ONE GPU -------------------------------------------
+# cudaIpc mappings work between processes that share a device, and the exchange kernels never call a collective
+# library, so a single-GPU box exercises mosaic_push_kernel / mosaic_wait_kernel / mosaic_guard_kernel too.  The
+# one-time handle exchange goes through a gloo group (NCCL refuses two ranks on one device).
+
+def _cpu_exchange_hooks():
+    """MosaicSlab hooks = the CUDA operators, with the halo / range exchange carried by CPU tensors (gloo)."""
+    import torch
+    from hipr_b200 import ops
+
+    def channel_sum(cube_slab):
+        s, mk = ops.channel_sum(cube_slab, None, normalize=False, dtype=torch.float64, return_max=True)
+        vmax, vmin = mk.values()
+        return s.cpu(), vmax.cpu(), vmin.cpu()
+
+    def score(ext, gmax, gmin, flavour):
+        keys = ops.MaxKey.from_values(gmax.cuda(), gmin.cuda()) if flavour not in ("F1", "F2") else None
+        return ops.lne2d_fixed(ext.cuda(), flavour, 11, 9, padded=False, range_keys=keys)
+
+    return {"channel_sum": channel_sum, "score": score, "accumulate": ops.cell_spectra_accumulate,
+            "finalize": ops.cell_spectra_finalize}
+
+
+def _one_gpu_worker_body(rank, world, port, tmp):
+    import torch
+    import torch.distributed as dist
+    for p in (ROOT, PKG):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(0)                   # every rank on the same device
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from hipr_b200 import sharding, synth
+    from oracle import hipr_oracle as O
+    Hm, Wm = 161, 256                          # uneven slabs
+    r0, r1 = sharding.slab_bounds(Hm, rank, world)
+    p2p = sharding.P2PMosaicSlab(r1 - r0, Wm)
+    ref = sharding.MosaicSlab(hooks=_cpu_exchange_hooks())
+    for step in range(4):                      # both parities, reused buffers
+        cube = synth.make_fov(Hm, Wm, 95, fov_index=40 + step)[0]
+        mine = cube[r0:r1].cuda()
+        got = p2p.score(mine, "F1", check=True)
+        assert torch.equal(got, ref.score(mine, "F1")), "peer-memory exchange differs from the reference exchange, step %d" % step
+        if step == 0:
+            want = O.neighbor2d_score(cube.numpy(), "F1")[r0:r1]
+            np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-5, atol=5e-7)
+    got3 = p2p.score(mine, "F3", check=True)   # F3 consumes the exchanged global range
+    assert torch.equal(got3, ref.score(mine, "F3"))
+    want3 = O.neighbor2d_score(cube.numpy(), "F3")[r0:r1]
+    np.testing.assert_allclose(got3.cpu().numpy(), want3, rtol=1e-5, atol=5e-7)
+    p2p.close()
+    # banded: exchange and stencil under the channel sum (hipr_mosaic_p2p_score)
+    big = synth.make_fov(4 * 96 * world, Wm, 95, fov_index=31)[0]
+    b0, b1 = sharding.slab_bounds(big.shape[0], rank, world)
+    p2p_big = sharding.P2PMosaicSlab(b1 - b0, Wm)
+    for fl in ("F1", "F2"):
+        for rep in range(3):
+            got_b = p2p_big.score(big[b0:b1].cuda(), fl, bands=4, check=True)
+        want_b = O.neighbor2d_score(big.numpy(), fl)[b0:b1]
+        np.testing.assert_allclose(got_b.cpu().numpy(), want_b, rtol=1e-5, atol=1e-6)   # atol: see _p2p_worker_body
+    p2p_big.close()
+    # a peer that never delivers: the wait kernel gives up, the score is poisoned, check_peers raises
+    late = sharding.P2PMosaicSlab(r1 - r0, Wm, timeout_ms=300.0)
+    if rank == 0:
+        out = late.score(mine, "F1")
+        assert bool(torch.isnan(out).all()), "a timed-out exchange must not return a score"
+        with pytest.raises(RuntimeError):
+            late.check_peers()
+    late.close()
+    open(os.path.join(tmp, "one%d" % rank), "w").write("ok")
+    dist.destroy_process_group()
+
+
+def _one_gpu_worker(rank, world, port, tmp):
+    _run_guarded(_one_gpu_worker_body, rank, world, port, tmp)
+
+
+def test_mosaic_peer_memory_two_ranks_one_gpu(torch_cuda, tmp_path):
+    """Runs on a single-GPU box: the peer-memory exchange between two processes that share cuda:0."""
+    _spawn(_one_gpu_worker, tmp_path, 29900 + (os.getpid() % 1000))
+    assert all((tmp_path / ("one%d" % r)).exists() for r in range(2))
