@@ -308,6 +308,13 @@ def measure_next_rows(cube, labels, with_cpu):
     out["e2e_chain_with_denoise"] = {"ms": 1e3 * (time.perf_counter() - t0) / 3, "mpix_s": npix / ((time.perf_counter() - t0) / 3) / 1e6,
                                      "api": "hipr_neighbor2d_host_denoise (pinned host cube -> score, lines 105-124 in full)"}
     del host
+    score = ops.neighbor2d_pipeline(cube, "F1")[0]
+    t = gpu_ms(lambda: ops.kmeans_threshold(score, 2), n=5)
+    km = ops.kmeans_threshold(score, 2)
+    out["kmeans_threshold_k2"] = {"ms": t, "n_iter": km.n_iter, "centers": [float(v) for v in km.cluster_centers_],
+                                  "note": "KMeans(2, random_state=0) on the 2048^2 score map incl. labels + mask + result readback"}
+    t = gpu_ms(lambda: ops.kmeans_threshold(score, 3), n=5)
+    out["kmeans_threshold_k3"] = {"ms": t, "n_iter": ops.kmeans_threshold(score, 3).n_iter}
     t = gpu_ms(lambda: ops.cell_geometry(labels, L))
     out["cell_geometry"] = {"ms": t, "cells": L}
     t = gpu_ms(lambda: ops.paint_labels(labels, lut, L))
@@ -324,6 +331,18 @@ def measure_next_rows(cube, labels, with_cpu):
         hipr_oracle.denoise_nl_means_2d(s64[:m, :m].cpu().numpy(), h=0.02)
         out["denoise_nl_means"]["cpu_ms_scaled"] = 1e3 * (time.perf_counter() - t0) * npix / (m * m)
         out["denoise_nl_means"]["cpu_note"] = "numpy restatement of skimage's fast mode on a %dx%d crop, scaled by pixels" % (m, m)
+        try:
+            s_np = score.cpu().numpy()
+            t0 = time.perf_counter()
+            c_sk, l_sk, m_sk, it_sk, _ = hipr_oracle.kmeans1d_sklearn(s_np, 2)
+            out["kmeans_threshold_k2"]["cpu_ms"] = 1e3 * (time.perf_counter() - t0)
+            out["kmeans_threshold_k2"]["parity"] = {
+                "oracle": "scikit-learn KMeans on the same float32 score map (whole FOV)",
+                "max_abs_center_diff": float(np.max(np.abs(c_sk - km.cluster_centers_))), "n_iter_equal": it_sk == km.n_iter,
+                "labels_differing": int((km.labels.cpu().numpy() != l_sk).sum()),
+                "mask_differing": int((km.mask.cpu().numpy() != m_sk).sum())}
+        except ImportError:
+            pass
         lab_np = labels[:n, :n].cpu().numpy()
         t0 = time.perf_counter()
         hipr_oracle.cell_geometry(lab_np)

@@ -41,6 +41,9 @@ _SIGNATURES = {
     "hipr_cell_moments": (_i, [_vp, _i, _i, _i, _i64, _vp, _vp]),
     "hipr_cell_geometry_finalize": (_i, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "hipr_paint_labels": (_i, [_vp, _i, _i64, _vp, _i, _i64, _i, _vp, _vp]),
+    "hipr_kmeans1d_workspace_bytes": (_i64, []),
+    "hipr_kmeans1d_uniforms": (_i, [_i, _i]),
+    "hipr_kmeans1d": (_i, [_vp, _i, _i64, _i, C.c_double, _i, _i, _i, _vp, _i, C.c_double, _vp, _vp, _i, _vp, _vp, _vp]),
     "hipr_mosaic_p2p_bytes": (_i64, [_i, _i, _i]),
     "hipr_p2p_alloc": (_i, [C.POINTER(_vp), _i64]),
     "hipr_p2p_free": (_i, [_vp]),

@@ -612,6 +612,66 @@ def paint_labels(labels, values, max_label=None):
 
 
 # ---------------------------------------------------------------------------------------------
+# 1-D k-means thresholding
+# ---------------------------------------------------------------------------------------------
+
+KMEANS_TRANSFORMS = {None: 0, "none": 0, "log10": 1, "log": 2}
+
+
+class KMeans1DResult:
+    """cluster_centers_ (k,), counts (k,), positive_means (k,), labels (int32 tensor, image shape) or None, mask
+    (bool tensor: the brightest cluster) or None, n_iter, inertia, bright (label of the brightest cluster),
+    n_samples, best_init."""
+
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
+def kmeans_threshold(image, n_clusters=2, random_state=0, n_init=1, transform=None, eps=0.0, positive_only=False,
+                     max_iter=300, tol=1e-4, return_labels=True, return_mask=True, fill_label=0):
+    """KMeans(n_clusters, random_state=random_state).fit_predict(f(image).reshape(-1, 1)) of scikit-learn 1.9 on the
+    device, plus the scripts' mask orientation (syn/...measurement.py:125-137): f = identity, log10(image + eps)
+    (transform='log10') or ln(image + eps) ('log'); positive_only: cluster image[image > 0] only, the other pixels
+    get fill_label / mask 0 (bio/...analysis.py:819).  image: float32 / float64 CUDA tensor of any shape.
+    Synchronises once (to read the 32-double result)."""
+    image = _dev(image, "image")
+    k = int(n_clusters)
+    if not isinstance(random_state, (int, np.integer)):
+        raise TypeError("random_state must be an integer seed (the reference passes 0)")
+    nu = lib().hipr_kmeans1d_uniforms(k, int(n_init))
+    check(nu if nu < 0 else 0, "kmeans_threshold")
+    # scikit-learn's draws, in its order: RandomState(seed).choice (one double) then uniform(size=trials) per seed
+    u = np.ascontiguousarray(np.random.RandomState(int(random_state)).random_sample(nu), dtype=np.float64)
+    try:
+        tcode = KMEANS_TRANSFORMS[transform]
+    except KeyError:
+        raise ValueError("transform must be None, 'log10' or 'log'")
+    dev = image.device
+    work = torch.empty(int(lib().hipr_kmeans1d_workspace_bytes()), dtype=torch.uint8, device=dev)
+    labels = torch.empty(image.shape, dtype=torch.int32, device=dev) if return_labels else None
+    mask = torch.empty(image.shape, dtype=torch.uint8, device=dev) if return_mask else None
+    res = torch.empty(32, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        check(lib().hipr_kmeans1d(C.c_void_p(image.data_ptr()), _DT[image.dtype], image.numel(), tcode, float(eps),
+                                  int(bool(positive_only)), k, int(n_init), u.ctypes.data_as(C.c_void_p), int(max_iter),
+                                  float(tol), C.c_void_p(work.data_ptr()),
+                                  C.c_void_p(labels.data_ptr()) if labels is not None else None, int(fill_label),
+                                  C.c_void_p(mask.data_ptr()) if mask is not None else None,
+                                  C.c_void_p(res.data_ptr()), _stream()), "kmeans_threshold")
+    r = res.cpu().numpy()
+    status = int(r[0])
+    if status == 2:
+        raise ValueError("Input X contains NaN or infinity.")          # scikit-learn's check_array message
+    if status == 4:
+        raise ValueError("n_samples=%d should be >= n_clusters=%d." % (int(r[1]), k))
+    if status == 3:
+        raise RuntimeError("a cluster ran empty during Lloyd iterations (scikit-learn would relocate it; not reproduced)")
+    return KMeans1DResult(cluster_centers_=r[8:8 + k].copy(), counts=r[16:16 + k].astype(np.int64),
+                          positive_means=r[24:24 + k].copy(), labels=labels, mask=mask.view(torch.bool) if mask is not None else None,
+                          n_iter=int(r[4]), inertia=float(r[5]), bright=int(r[7]), n_samples=int(r[1]), best_init=int(r[6]))
+
+
+# ---------------------------------------------------------------------------------------------
 # host-buffer (numpy) entry points: copies happen inside the library
 # ---------------------------------------------------------------------------------------------
 

@@ -286,6 +286,34 @@ int hipr_cell_geometry_finalize(const uint64_t *moments_dev, int64_t max_label, 
 int hipr_paint_labels(const void *labels_dev, int label_bytes, int64_t npix, const void *values_dev, int K,
                       int64_t max_label, int dtype, void *out_dev, void *stream);
 
+/* ---- 1-D k-means thresholding ---------------------------------------------------------------------------
+ * Replaces KMeans(n_clusters = k, random_state = seed).fit_predict(image.reshape(-1, 1)) on the score map, the
+ * denoised sum image or their logarithms, and the mask orientation that follows it:
+ *   syn/..._measurement.py:125-149; bio/..._analysis.py:367-392, 463-486, 819-846, 1128-1156;
+ *   eco/..._measurement.py:73-85 (log(sum + 1e-2)); ref/..._measurement.py:112-124.
+ * Oracle: scikit-learn 1.9.0 (k-means++ seeding, Lloyd, tol = 1e-4 * var, labels from the final centres, best of
+ * n_init by inertia).  scikit-learn's random draws are data independent in number, so the CALLER draws them:
+ *   uniforms_host = numpy.random.RandomState(seed).random_sample(hipr_kmeans1d_uniforms(k, n_init))
+ * (per initialisation: 1 for the first seed, then 2 + int(log(k)) per further seed).
+ *   image_dev     (n) of dtype; sample value = image (transform 0), log10(image + eps) (1) or ln(image + eps) (2),
+ *                 computed in float64; positive_only != 0: only samples with image > 0 take part (the
+ *                 `image_final[image_final > 0]` call sites), in raster order
+ *   workspace_dev hipr_kmeans1d_workspace_bytes() bytes of device scratch
+ *   labels_out_dev NULL or (n) int32: scikit-learn's label of every sample; fill_label where positive_only excludes it
+ *   mask_out_dev  NULL or (n) uint8: 1 where the sample belongs to the cluster with the largest mean of its positive
+ *                 image values (the scripts' `i0 < i1` / np.argmax([i0, i1, i2]) orientation), else 0
+ *   result_dev    32 doubles: [0] status (0 ok; 2 non-finite sample; 3 a cluster ran empty; 4 fewer samples than k),
+ *                 [1] samples used, [2] their mean, [3] absolute tolerance, [4] Lloyd iterations, [5] inertia,
+ *                 [6] index of the winning initialisation, [7] label of the brightest cluster,
+ *                 [8..8+k) cluster_centers_, [16..16+k) cluster sizes, [24..24+k) mean of the positive image values
+ * One cooperative launch (csrc/kmeans1d.cu); k <= 8; k * n_init bounded by hipr_kmeans1d_uniforms (HIPR_E_RANGE).
+ */
+int64_t hipr_kmeans1d_workspace_bytes(void);
+int hipr_kmeans1d_uniforms(int k, int n_init);
+int hipr_kmeans1d(const void *image_dev, int dtype, int64_t n, int transform, double eps, int positive_only, int k,
+                  int n_init, const double *uniforms_host, int max_iter, double tol, void *workspace_dev,
+                  int32_t *labels_out_dev, int fill_label, uint8_t *mask_out_dev, double *result_dev, void *stream);
+
 /* ---- split mosaic over NVLink peer memory (BASELINE config 5) -------------------------------------------
  * The reference has no multi-GPU path; this is the exchange step of a stitched mosaic cut into row slabs, done by
  * this library's kernels through peer-mapped memory instead of a collective library (csrc/mosaic_p2p.cu).

@@ -6,7 +6,7 @@ product.  Only tests/, __graft_entry__.smoke() and bench.py's CPU legs import it
 
 Parity status: PINNED.  The reference ships no tests or golden vectors, but
 its native stencils compile here unmodified (oracle/build_ref.py -> oracle/_ref/), and
-tests/test_oracle_vs_ref.py checks every function below against that compiled reference;
+tests/test_oracle.py checks every function below against that compiled reference;
 tests/golden/ freezes vectors generated from it (tests/golden/make_golden.py) so the pin
 also holds on the GPU box where /root/reference is absent.  The per-cell reduction follows
 scikit-image's regionprops (third-party, NOT vendored in the reference, version not pinned
@@ -522,3 +522,104 @@ def paint_labels(seg, values):
     for L in np.unique(seg[seg > 0]):
         out[seg == L] = values[L]
     return out
+
+
+# --------------------------------------------------------------------------------------------
+# 1-D k-means thresholding
+# --------------------------------------------------------------------------------------------
+
+def _kmeans_samples(image, transform=None, eps=0.0, positive_only=False):
+    img = np.asarray(image, dtype=np.float64)
+    valid = (img > 0) if positive_only else np.ones(img.shape, dtype=bool)
+    x = img[valid]
+    if transform == "log10":
+        x = np.log10(x + eps)
+    elif transform == "log":
+        x = np.log(x + eps)
+    return img, valid, x
+
+
+def _kmeans_finish(img, valid, labels_valid, k, fill_label=0):
+    """Full-size label image, and the scripts' orientation: the cluster with the largest mean of its positive image
+    values is the foreground (syn/..._measurement.py:126-135: `image0 = image_final*(seg == 0)`,
+    `i0 = np.average(image0[image0 > 0])`, `if i0 < i1: mask = seg == 1`; np.argmax([i0, i1, i2]) at bio/...:471)."""
+    labels = np.full(img.shape, fill_label, dtype=np.int32)
+    labels[valid] = labels_valid
+    pm = np.full(k, -np.inf)
+    for j in range(k):
+        sel = valid & (labels == j) & (img > 0)
+        if sel.any():
+            pm[j] = img[sel].mean()
+    bright = int(np.argmax(pm))
+    return labels, valid & (labels == bright), pm, bright
+
+
+def kmeans1d_sklearn(image, n_clusters=2, random_state=0, n_init=1, transform=None, eps=0.0, positive_only=False):
+    """THE pinned oracle of this row: scikit-learn itself (1.9.0 in this image), called as the scripts call it:
+    KMeans(n_clusters = k, random_state = 0).fit_predict(x.reshape(-1, 1))  (syn/..._measurement.py:125, 141;
+    bio/..._analysis.py:367, 384, 463, 819, 830; eco/..._measurement.py:73, 85).  n_init=1 is scikit-learn >= 1.4's
+    'auto' for k-means++; the reference's era used 10.
+    Returns (cluster_centers_ (k,), labels (image shape, int32), foreground mask, n_iter, inertia)."""
+    from sklearn.cluster import KMeans
+    img, valid, x = _kmeans_samples(image, transform, eps, positive_only)
+    km = KMeans(n_clusters=n_clusters, random_state=random_state, n_init=n_init).fit(x.reshape(-1, 1))
+    labels, mask, _, _ = _kmeans_finish(img, valid, km.labels_, n_clusters)
+    return km.cluster_centers_.ravel().copy(), labels, mask, int(km.n_iter_), float(km.inertia_)
+
+
+def kmeans1d(image, n_clusters=2, random_state=0, n_init=1, transform=None, eps=0.0, positive_only=False, max_iter=300,
+             tol=1e-4):
+    """numpy restatement of what scikit-learn 1.9.0's KMeans does on one feature (sklearn/cluster/_kmeans.py:
+    fit -> _kmeans_plusplus -> _kmeans_single_lloyd), checked label for label against kmeans1d_sklearn in
+    tests/test_oracle.py.  It documents exactly what the CUDA kernel reproduces:
+      * X is centred by its mean; tol_abs = tol * var(X);
+      * seeding: first seed = sample floor(u0 * n) (RandomState.choice with uniform p); every further seed: `trials`
+        = 2 + int(log(k)) candidates at searchsorted(cumsum(closest_dist_sq), u * current_pot), keep the one with the
+        smallest new potential;
+      * Lloyd: label = argmin_j(c_j^2 - 2 x c_j) (first minimum), centres = cluster means; stop when the labels did not
+        change (in 1-D: the cluster sizes) or sum((c_new - c_old)^2) <= tol_abs; labels are then those of the final centres;
+      * best of n_init by inertia (first wins ties).
+    Returns like kmeans1d_sklearn."""
+    img, valid, x = _kmeans_samples(image, transform, eps, positive_only)
+    k, n = int(n_clusters), x.size
+    trials = 2 + int(np.log(k))
+    u = np.random.RandomState(random_state).random_sample(n_init * (1 + trials * (k - 1)))
+    mean = x.mean()
+    xc = x - mean
+    tol_abs = np.var(x) * tol
+    best, ui = None, 0
+    for _ in range(n_init):
+        cid = min(int(np.floor(u[ui] * n)), n - 1)
+        ui += 1
+        centers = [xc[cid]]
+        closest = (xc - centers[0]) ** 2
+        pot = closest.sum()
+        for _c in range(1, k):
+            r = u[ui:ui + trials] * pot
+            ui += trials
+            cand = np.clip(np.searchsorted(np.cumsum(closest), r), None, n - 1)
+            d = np.minimum(closest[None, :], (xc[None, :] - xc[cand][:, None]) ** 2)
+            pots = d.sum(axis=1)
+            b = int(np.argmin(pots))
+            pot, closest = pots[b], d[b]
+            centers.append(xc[cand[b]])
+        centers = np.array(centers)
+        counts_old = None
+        for it in range(max_iter):
+            lab = np.argmin(centers[None, :] ** 2 - 2 * xc[:, None] * centers[None, :], axis=1)
+            counts = np.bincount(lab, minlength=k)
+            new = np.bincount(lab, weights=xc, minlength=k) / counts
+            shift = ((new - centers) ** 2).sum()
+            centers = new
+            if counts_old is not None and np.array_equal(counts, counts_old):
+                break
+            if shift <= tol_abs:
+                break
+            counts_old = counts
+        lab = np.argmin(centers[None, :] ** 2 - 2 * xc[:, None] * centers[None, :], axis=1)
+        inertia = float(((xc - centers[lab]) ** 2).sum())
+        if best is None or (inertia < best[0] and not np.array_equal(np.sort(np.bincount(lab, minlength=k)[np.argsort(centers)]),
+                                                                      np.sort(best[4]))):
+            best = (inertia, centers + mean, lab, it + 1, np.bincount(lab, minlength=k)[np.argsort(centers)])
+    labels, mask, _, _ = _kmeans_finish(img, valid, best[2], k)
+    return best[1], labels, mask, best[3], best[0]
