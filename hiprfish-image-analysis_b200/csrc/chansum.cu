@@ -35,7 +35,7 @@ constexpr int CS_INFLIGHT_TARGET = 150 * 1024;
 // InT: float, or raw detector counts (uint16_t / uint8_t) converted on the fly as python-bioformats'
 // rescale does, float32(count) / float32(scale) per sample (raw_value); half / a quarter of the bytes.
 template <typename OutT, bool CALIB, typename InT>
-__global__ void __launch_bounds__(CS_MAX_THREADS, 1)
+__global__ void __launch_bounds__(CS_MAX_THREADS, 2)   // 2: caps the kernel at 60 registers (56 used, no spills) so that 4 stencil CTAs of the previous field of view fit beside its one CTA per SM
 chansum_bulk_kernel(const InT *__restrict__ cube, const float *__restrict__ calib, int64_t nchunks, int C, int cpx,
                     int stages, int groups, float scale, OutT *__restrict__ out,
                     unsigned long long *__restrict__ maxkey) {
@@ -247,8 +247,10 @@ static int chansum_launch(const InT *cube, const float *calib, int64_t npix, int
                 if (calib) {
                     static std::atomic<uint64_t> attr_c{0};
                     auto kern = chansum_bulk_kernel<OutT, true, float>;
-                    if (first_use_on_device(attr_c))
+                    if (first_use_on_device(attr_c)) {
                         HIPR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM_BUDGET));
+                        HIPR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+                    }
                     kern<<<(unsigned)grid, threads, smem, st>>>(cube, calib, nchunks, C, cpx, stages, groups, scale, out,
                                                                maxkey);
                 }
@@ -256,8 +258,14 @@ static int chansum_launch(const InT *cube, const float *calib, int64_t npix, int
             if (!calib) {
                 static std::atomic<uint64_t> attr_n{0};
                 auto kern = chansum_bulk_kernel<OutT, false, InT>;
-                if (first_use_on_device(attr_n))
+                if (first_use_on_device(attr_n)) {
                     HIPR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM_BUDGET));
+                    // The SM keeps the shared-memory carve-out of the kernel that configured it while that kernel is
+                    // resident.  This kernel needs 146 KB, which selects the 164 KB configuration and leaves 17 KB for
+                    // the stencil CTAs of the previous field of view that run beside it; asking for the largest
+                    // carve-out (it uses no L1: its data arrives by bulk copies) leaves them 81 KB.
+                    HIPR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+                }
                 kern<<<(unsigned)grid, threads, smem, st>>>(cube, nullptr, nchunks, C, cpx, stages, groups, scale, out,
                                                            maxkey);
             }

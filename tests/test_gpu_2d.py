@@ -388,3 +388,19 @@ def test_host_entry_point_pageable_equals_pinned(torch_cuda):
     assert np.array_equal(a, b)
     dev = hipr_b200.neighbor2d_score(torch_cuda.from_numpy(cube).cuda(), "F1").cpu().numpy()
     assert np.array_equal(a, dev)                                          # and the same as the device-resident call
+
+
+@pytest.mark.parametrize("flavour", ["F1", "F2", "F3"])
+def test_score_strict_relative_parity(torch_cuda, oracle, flavour):
+    """north_star's gate as written: 1e-5 RELATIVE, no absolute term, over a whole 512^2 FOV.  The fixed-point
+    stencil alone cannot give it (a pixel that is almost the minimum of its lines keeps the grid's absolute error);
+    the pixels it marks as ill-conditioned are recomputed in float64 (lne2d_refine_kernel)."""
+    import hipr_b200
+    from hipr_b200 import synth
+    cube, _, _ = synth.make_fov(512, 512, 95, fov_index=5)
+    want = oracle.neighbor2d_score(cube.numpy(), flavour)
+    for got in (hipr_b200.neighbor2d_score(cube.cuda(), flavour).cpu().numpy(),
+                hipr_b200.neighbor2d_score_host(cube.numpy(), flavour)):
+        assert (got >= 0).all(), "a refinement sentinel survived"
+        np.testing.assert_allclose(got, want, rtol=1e-5, atol=0)
+        assert np.array_equal(got == 0, want == 0)

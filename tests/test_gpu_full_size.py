@@ -47,7 +47,7 @@ def test_config2_windows_against_the_oracle(torch_cuda, oracle, fov2048):
         r0, r1, c0, c1 = max(r - 5, 0), min(r + 96 + 5, 2048), max(c - 5, 0), min(c + 128 + 5, 2048)
         crop = cube[r0:r1, c0:c1].cpu().numpy()
         want = oracle.neighbor2d_score(crop, "F1")[r - r0: r - r0 + 96, c - c0: c - c0 + 128]
-        np.testing.assert_allclose(full[r:r + 96, c:c + 128], want, rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(full[r:r + 96, c:c + 128], want, rtol=RTOL, atol=0)    # strictly relative
 
 
 def test_config2_properties(torch_cuda, fov2048):
