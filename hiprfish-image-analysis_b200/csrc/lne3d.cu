@@ -6,6 +6,7 @@
 // shared memory (z fastest, lanes along z: conflict-free), each thread walks TX voxels.  The
 // 792-entry offset table rides in the kernel parameter bank.  This kernel is shared-memory /
 // min-max-ALU bound (792 samples + a 72-value rank selection per voxel), not HBM bound.
+#include <cstdlib>
 #include <type_traits>
 #include "hipr_common.cuh"
 #include "lne_math.cuh"
@@ -43,6 +44,27 @@ __device__ __forceinline__ void l3_static_for(F &&f) {
         l3_static_for<I + 1, N>(f);
     }
 }
+// Lines of the pinned table that repeat an earlier line (same 11 voxels, in either order): 6 of the 72.  Their
+// min, max and centre are the earlier line's, so their value is copied instead of recomputed.
+constexpr int l3_dup_of(int t) {
+    for (int u = 0; u < t; ++u) {
+        bool same = true, rev = true;
+        for (int li = 0; li < L3_P; ++li) {
+            same = same && (l3_baked_off(t, li) == l3_baked_off(u, li));
+            rev = rev && (l3_baked_off(t, li) == l3_baked_off(u, L3_P - 1 - li));
+        }
+        if (same || rev) return u;
+    }
+    return -1;
+}
+
+constexpr int l3_mult(int t) {      // 1 + number of later lines that repeat line t
+    int m = 1;
+    for (int u = t + 1; u < L3_T; ++u)
+        if (l3_dup_of(u) == t) ++m;
+    return m;
+}
+
 // float32 lines use the fast reciprocal divide (2 ulp): one of 72 per voxel, far inside the gate
 template <typename T> __device__ __forceinline__ T l3_div(T a, T b) { return a / b; }
 template <> __device__ __forceinline__ float l3_div<float>(float a, float b) { return __fdividef(a, b); }
@@ -150,19 +172,87 @@ lne3d_p11t72_kernel(const T *__restrict__ vol, int Xs, int Ys, int Zs, int src_o
 // ---------------------------------------------------------------------------------------
 constexpr uint32_t L3Q_BIAS = 0x00800000u;
 constexpr double L3Q_SPAN = (double)0x7E000000u;
+// Strict relative parity, as in 2-D (csrc/lne2d_q.cu): a line value r_t = dq_t / den_t is off by at most
+// (1 + r_t) e_t, e_t = 1 / den_t in grid units; the bound is propagated through mean * (2 lq) / (uq + lq) with e_max,
+// the largest e_t, standing in for the e of the quartile lines, and a voxel whose bound exceeds L3Q_REFINE_THR is
+// written as a sentinel and recomputed in float64 by lne3d_refine_kernel (~2 % of a synthetic z-stack).
+constexpr float L3Q_REFINE_THR = 8e-6f;
+constexpr float L3Q_SENTINEL = -2.0f;
 
-template <typename SrcT, int FLAVOUR, int MODE, int TX>
+// mean * (1 - qcv) over the 72 directions without the cancellation of 1 - (uq - lq) / (uq + lq)
+struct L3QResult {
+    float score, mean, r17, r18, r53, r54;
+    bool mark;
+};
+template <int FLAVOUR>
+__device__ __forceinline__ void l3q_factor(float lq, float uq, float &A, float &B, bool &unit, float &factor) {
+    unit = false;
+    if (FLAVOUR == HIPR_FLAVOUR_F3) {
+        A = 2.f * lq + 1e-8f;
+        B = uq + lq + 1e-8f;
+        factor = __fdiv_rn(A, B);
+    } else {                       // F2, ME2: qcv = nan_to_num((uq - lq) / (uq + lq)); 0 / 0 -> 0 -> factor 1
+        A = 2.f * lq;
+        B = uq + lq;
+        unit = (B == 0.f);
+        factor = unit ? 1.f : __fdiv_rn(A, B);
+    }
+}
+template <int FLAVOUR, bool REFINE>
+__device__ __forceinline__ L3QResult l3q_reduce(float (&r)[L3_T], float e_max) {
+    L3QResult res;
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < L3_T; ++i) sum += r[i];
+    const float mean = sum * (1.0f / L3_T);
+    sort_network<float, L3_T>(r);
+    const float lq = quartile_sorted<float, L3_T, 1>(r);
+    const float uq = quartile_sorted<float, L3_T, 3>(r);
+    float A, B, factor;
+    bool unit;
+    l3q_factor<FLAVOUR>(lq, uq, A, B, unit, factor);
+    res.score = mean * factor;
+    res.mean = mean;
+    res.r17 = r[17];
+    res.r18 = r[18];
+    res.r53 = r[53];
+    res.r54 = r[54];
+    res.mark = false;
+    if (REFINE) {
+        // first opinion: e_max, the largest e_t of the voxel, stands in for the e of the quartile lines
+        const float d_mean = fmaf(mean, e_max, e_max);
+        if (unit) res.mark = d_mean > L3Q_REFINE_THR * mean;
+        else {
+            const float d_lq = (lq > 0.f) ? fmaf(lq, e_max, e_max) : 0.f;
+            const float d_uq = (uq > 0.f) ? fmaf(uq, e_max, e_max) : 0.f;
+            res.mark = fmaf(mean, 2.f * d_lq * B + (d_lq + d_uq) * A, d_mean * A * B) > L3Q_REFINE_THR * A * B * mean;
+        }                                    // NaN (a flat line, F2) compares false and stays NaN
+    }
+    return res;
+}
+
+// a voxel the first opinion marked, parked for the second opinion
+struct L3QPending {
+    float score, mean, r17, r18, r53, r54;
+    int local;                               // (lx * L3_TY + ty) * L3_TZ + tz
+};
+constexpr int L3Q_PENDING = 224;             // per CTA; beyond that a marked voxel goes straight to the refinement
+
+template <typename SrcT, int FLAVOUR, int MODE, int TX, bool REFINE>
 __global__ void __launch_bounds__(256)
 lne3d_q_kernel(const SrcT *__restrict__ vol, int Xs, int Ys, int Zs, int src_off, int X, int Y, int Z,
                const unsigned long long *__restrict__ maxkey, float *__restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem_raw3q[];
     float *tile = reinterpret_cast<float *>(smem_raw3q);
     __shared__ double red[16];
+    __shared__ L3QPending pending[(REFINE && MODE == 1) ? L3Q_PENDING : 1];
+    __shared__ unsigned int n_pending;
     constexpr int SX = TX + L3_P - 1;
     const int nzb = (Z + L3_TZ - 1) / L3_TZ;
     const int z0 = (blockIdx.x % nzb) * L3_TZ;
     const int y0 = (blockIdx.x / nzb) * L3_TY;
     const int x0 = blockIdx.y * TX;
+    if (threadIdx.x == 0) n_pending = 0;
     double bmax = -__longlong_as_double(0x7ff0000000000000ll), bmin = -bmax;
     for (int i = threadIdx.x; i < SX * L3_SY * L3_SZ; i += 256) {
         const int lz = i % L3_SZ, rest = i / L3_SZ;
@@ -204,39 +294,250 @@ lne3d_q_kernel(const SrcT *__restrict__ vol, int Xs, int Ys, int Zs, int src_off
     __syncthreads();
     const int tz = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int z = z0 + tz, y = y0 + ty;
-    if (z >= Z || y >= Y) return;
+    // one line of the fixed-point tile: value and e = 1 / (denominator in grid units)
+    auto line = [&](const float *base, auto tc, float &rv, float &inv) {
+        constexpr int t = decltype(tc)::value;
+        constexpr int o0 = l3_baked_off(t, 0);
+        float mn = base[o0], mx = mn;
+        l3_static_for<1, L3_P>([&](auto lc) {
+            constexpr int off = l3_baked_off(t, decltype(lc)::value);
+            const float s = base[off];
+            mn = fminf(mn, s);
+            mx = fmaxf(mx, s);
+        });
+        constexpr int oc = l3_baked_off(t, L3_HALF);
+        const float c = base[oc];
+        const float dq = __uint2float_rn(__float_as_uint(c) - __float_as_uint(mn));
+        const float rq = __uint2float_rn(__float_as_uint(mx) - __float_as_uint(mn));
+        float den;
+        if (FLAVOUR == HIPR_FLAVOUR_F2) den = rq;                         // 0/0 -> NaN on a flat line
+        else if (FLAVOUR == HIPR_FLAVOUR_F3) den = rq + eps_q;
+        else den = fmaxf(rq, eps_q);
+        inv = __fdividef(1.0f, den);
+        rv = dq * inv;
+    };
+    if (z < Z && y < Y) {
 #pragma unroll 1
-    for (int lx = 0; lx < TX; ++lx) {
-        const int x = x0 + lx;
-        if (x >= X) break;
-        const float *base = tile + (lx * L3_SY + ty) * L3_SZ + tz;
-        float r[L3_T];
+        for (int lx = 0; lx < TX; ++lx) {
+            const int x = x0 + lx;
+            if (x >= X) break;
+            const float *base = tile + (lx * L3_SY + ty) * L3_SZ + tz;
+            float r[L3_T];
+            float e_max = 0.f;
+            l3_static_for<0, L3_T>([&](auto tc) {
+                constexpr int t = decltype(tc)::value;
+                constexpr int dup = l3_dup_of(t);
+                if constexpr (dup >= 0) {
+                    r[t] = r[dup];
+                } else {
+                    float rv, inv;
+                    line(base, tc, rv, inv);
+                    if (REFINE) {
+                        if (MODE == 0) {
+                            // per-direction output: mark the value itself when (1 + r) e > thr * r
+                            if (rv > 0.f && fmaf(rv, inv, inv) > L3Q_REFINE_THR * rv) rv = L3Q_SENTINEL;
+                        } else {
+                            e_max = fmaxf(e_max, inv);
+                        }
+                    }
+                    r[t] = rv;
+                }
+            });
+            const int64_t v = ((int64_t)x * Y + y) * Z + z;
+            if (MODE == 0) {
+                float *o = out + v * L3_T;
+#pragma unroll
+                for (int t = 0; t < L3_T; ++t) o[t] = r[t];
+            } else {
+                const L3QResult res = l3q_reduce<FLAVOUR, REFINE>(r, e_max);
+                float score = res.score;
+                if (REFINE && res.mark) {
+                    const unsigned int slot = atomicAdd(&n_pending, 1u);
+                    if (slot < L3Q_PENDING) {
+                        pending[slot] = L3QPending{res.score, res.mean, res.r17, res.r18, res.r53, res.r54,
+                                                   (lx * L3_TY + ty) * L3_TZ + tz};
+                        continue;                       // written after the second opinion
+                    }
+                    score = L3Q_SENTINEL;
+                }
+                out[v] = score;
+            }
+        }
+    }
+    if (!(REFINE && MODE == 1)) return;
+    // ---- second opinion for the marked voxels, packed into full warps: the 72 lines again, this time keeping the e of
+    // the lines that gave the quartile order statistics and the exact sum for the mean -------------------------------
+    __syncthreads();
+    const int np = (int)min(n_pending, (unsigned int)L3Q_PENDING);
+    for (int p = threadIdx.x; p < np; p += 256) {
+        const L3QPending pd = pending[p];
+        const int ptz = pd.local % L3_TZ, rest = pd.local / L3_TZ;
+        const int pty = rest % L3_TY, plx = rest / L3_TY;
+        const float *base = tile + (plx * L3_SY + pty) * L3_SZ + ptz;
+        float e17 = 0.f, e18 = 0.f, e53 = 0.f, e54 = 0.f, d_sum = 0.f;
         l3_static_for<0, L3_T>([&](auto tc) {
             constexpr int t = decltype(tc)::value;
-            constexpr int o0 = l3_baked_off(t, 0);
-            float mn = base[o0], mx = mn;
-            l3_static_for<1, L3_P>([&](auto lc) {
-                constexpr int off = l3_baked_off(t, decltype(lc)::value);
-                const float s = base[off];
-                mn = fminf(mn, s);
-                mx = fmaxf(mx, s);
-            });
-            constexpr int oc = l3_baked_off(t, L3_HALF);
-            const float c = base[oc];
-            const float dq = __uint2float_rn(__float_as_uint(c) - __float_as_uint(mn));
-            const float rq = __uint2float_rn(__float_as_uint(mx) - __float_as_uint(mn));
-            if (FLAVOUR == HIPR_FLAVOUR_F2) r[t] = __fdividef(dq, rq);            // 0/0 -> NaN on a flat line
-            else if (FLAVOUR == HIPR_FLAVOUR_F3) r[t] = __fdividef(dq, rq + eps_q);
-            else r[t] = __fdividef(dq, fmaxf(rq, eps_q));
+            if constexpr (l3_dup_of(t) < 0) {
+                float rv, inv;
+                line(base, tc, rv, inv);
+                constexpr float mult = (float)l3_mult(t);
+                d_sum += (rv > 0.f) ? mult * fmaf(rv, inv, inv) : 0.f;
+                e17 = (rv == pd.r17) ? fmaxf(e17, inv) : e17;
+                e18 = (rv == pd.r18) ? fmaxf(e18, inv) : e18;
+                e53 = (rv == pd.r53) ? fmaxf(e53, inv) : e53;
+                e54 = (rv == pd.r54) ? fmaxf(e54, inv) : e54;
+            }
         });
-        const int64_t v = ((int64_t)x * Y + y) * Z + z;
-        if (MODE == 0) {
-            float *o = out + v * L3_T;
+        const float lq = quartile_pair<float, 1>(pd.r17, pd.r18), uq = quartile_pair<float, 3>(pd.r53, pd.r54);
+        float A, B, factor;
+        bool unit;
+        l3q_factor<FLAVOUR>(lq, uq, A, B, unit, factor);
+        const float d_mean = d_sum * (1.0f / L3_T);
+        // |d lq| <= 0.25 (1 + r17) e17 + 0.75 (1 + r18) e18, |d uq| <= 0.75 (1 + r53) e53 + 0.25 (1 + r54) e54
+        const float d_lq = 0.25f * ((pd.r17 > 0.f) ? fmaf(pd.r17, e17, e17) : 0.f) + 0.75f * ((pd.r18 > 0.f) ? fmaf(pd.r18, e18, e18) : 0.f);
+        const float d_uq = 0.75f * ((pd.r53 > 0.f) ? fmaf(pd.r53, e53, e53) : 0.f) + 0.25f * ((pd.r54 > 0.f) ? fmaf(pd.r54, e54, e54) : 0.f);
+        bool mark;
+        if (unit) mark = d_mean > L3Q_REFINE_THR * pd.mean;
+        else mark = fmaf(pd.mean, 2.f * d_lq * B + (d_lq + d_uq) * A, d_mean * A * B) > L3Q_REFINE_THR * A * B * pd.mean;
+        const int64_t v = ((int64_t)(x0 + plx) * Y + (y0 + pty)) * Z + (z0 + ptz);
+        out[v] = mark ? L3Q_SENTINEL : pd.score;
+    }
+}
+
+// the pinned table for run-time indexing on the device (kBaked3D itself only exists in constant expressions)
+struct Baked3DCopy {
+    int v[L3_T * L3_P * 3];
+};
+constexpr Baked3DCopy make_baked3d_copy() {
+    Baked3DCopy a{};
+    for (int i = 0; i < L3_T * L3_P * 3; ++i) a.v[i] = kBaked3D[i];
+    return a;
+}
+__constant__ Baked3DCopy c_baked3d = make_baked3d_copy();
+
+// One line value in float64 from the source volume (edge clamp, NaN -> 0: the fixed-point loader's semantics);
+// `tab` = the (72, 11, 3) table as bytes.
+template <typename SrcT, int FLAVOUR>
+__device__ __forceinline__ double l3_line_value_f64(const SrcT *__restrict__ vol, int Xs, int Ys, int Zs, int bx, int by,
+                                                   int bz, const signed char *__restrict__ tab, int t, double eps) {
+    double v[L3_P];
 #pragma unroll
-            for (int t = 0; t < L3_T; ++t) o[t] = r[t];
-        } else {
-            out[v] = reduce_dirs<float, L3_T, FLAVOUR>(r);
+    for (int li = 0; li < L3_P; ++li) {
+        const signed char *o = tab + (t * L3_P + li) * 3;
+        const int sx = min(max(bx + o[0], 0), Xs - 1), sy = min(max(by + o[1], 0), Ys - 1), sz = min(max(bz + o[2], 0), Zs - 1);
+        const double s = (double)vol[((int64_t)sx * Ys + sy) * Zs + sz];
+        v[li] = (s != s) ? 0.0 : s;
+    }
+    double mn = v[0], mx = v[0];
+#pragma unroll
+    for (int li = 1; li < L3_P; ++li) {
+        mn = fmin(mn, v[li]);
+        mx = fmax(mx, v[li]);
+    }
+    double den = mx - mn;
+    if (FLAVOUR == HIPR_FLAVOUR_F3) den += eps;
+    else if (FLAVOUR != HIPR_FLAVOUR_F2) den = fmax(den, eps);
+    return (v[L3_HALF] - mn) / den;
+}
+
+// Refinement of the marked voxels of a fused score volume, in float64.  A CTA scans 16384 consecutive voxels for the
+// sentinel, collects them in shared memory and takes 4 per round with 72 threads per voxel: phase A, thread t
+// computes the value of line t; phase B, thread t counts the values below its own (ties by index): the threads that
+// hold ranks 17, 18, 53 and 54 publish them, thread 0 of the voxel adds up the mean and writes the score.  Small
+// register and shared-memory footprint, so many CTAs are resident.
+constexpr int RF3_SPAN = 16384, RF3_VOX = 4, RF3_THREADS = RF3_VOX * L3_T;   // 288
+
+template <typename SrcT, int FLAVOUR>
+__global__ void __launch_bounds__(RF3_THREADS, 3)
+lne3d_refine_kernel(const SrcT *__restrict__ vol, int Xs, int Ys, int Zs, int src_off, int X, int Y, int Z,
+                    const unsigned long long *__restrict__ maxkey, float *__restrict__ out) {
+    __shared__ double rbuf[RF3_VOX][L3_T];
+    __shared__ double sel[RF3_VOX][4];
+    __shared__ int has_nan[RF3_VOX];
+    __shared__ signed char tab[L3_T * L3_P * 3];
+    __shared__ unsigned short marked[RF3_SPAN];
+    __shared__ unsigned int n_marked;
+    const int64_t nvox = (int64_t)X * Y * Z;
+    const int64_t v0 = (int64_t)blockIdx.x * RF3_SPAN;
+    if (threadIdx.x == 0) n_marked = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < RF3_SPAN; i += RF3_THREADS)
+        if (v0 + i < nvox && out[v0 + i] == L3Q_SENTINEL) marked[atomicAdd(&n_marked, 1u)] = (unsigned short)i;
+    __syncthreads();
+    const int n = (int)n_marked;
+    if (n == 0) return;
+    for (int i = threadIdx.x; i < L3_T * L3_P * 3; i += RF3_THREADS) tab[i] = (signed char)c_baked3d.v[i];
+    const double eps = 1e-8 * (maxkey ? fabs(double_of_key(*maxkey)) : 1.0);
+    const int j = threadIdx.x / L3_T, t = threadIdx.x - j * L3_T;
+    for (int j0 = 0; j0 < n; j0 += RF3_VOX) {
+        const bool active = (j0 + j < n);
+        __syncthreads();                     // table staged; previous round's buffers consumed
+        double mine = 0.0;
+        int64_t v = 0;
+        if (active) {
+            v = v0 + marked[j0 + j];
+            const int z = (int)(v % Z);
+            const int64_t rest = v / Z;
+            const int y = (int)(rest % Y), x = (int)(rest / Y);
+            mine = l3_line_value_f64<SrcT, FLAVOUR>(vol, Xs, Ys, Zs, x - L3_HALF + src_off, y - L3_HALF + src_off,
+                                                    z - L3_HALF + src_off, tab, t, eps);
+            rbuf[j][t] = mine;
+            if (t == 0) has_nan[j] = 0;
         }
+        __syncthreads();
+        if (active) {
+            if (mine != mine) has_nan[j] = 1;
+            int below = 0;
+#pragma unroll 4
+            for (int u = 0; u < L3_T; ++u) {
+                const double o = rbuf[j][u];
+                below += (o < mine || (o == mine && u < t)) ? 1 : 0;
+            }
+            if (below == 17) sel[j][0] = mine;
+            if (below == 18) sel[j][1] = mine;
+            if (below == 53) sel[j][2] = mine;
+            if (below == 54) sel[j][3] = mine;
+        }
+        __syncthreads();
+        if (active && t == 0) {
+            double sum = 0.0;
+#pragma unroll 4
+            for (int u = 0; u < L3_T; ++u) sum += rbuf[j][u];
+            const double mean = sum / L3_T;
+            // numpy 'linear' percentiles at virtual indices 17.75 and 53.25 (numpy's _lerp)
+            const double a1 = sel[j][0], b1 = sel[j][1], a3 = sel[j][2], b3 = sel[j][3];
+            const double lq = b1 - (b1 - a1) * 0.25, uq = a3 + (b3 - a3) * 0.25;
+            double score;
+            if (has_nan[j]) score = __longlong_as_double(0x7ff8000000000000ll);
+            else if (FLAVOUR == HIPR_FLAVOUR_F3) score = mean * (1.0 - (uq - lq) / (uq + lq + 1e-8));
+            else {
+                const double qcv = (uq + lq == 0.0) ? 0.0 : (uq - lq) / (uq + lq);     // nan_to_num(0 / 0) = 0
+                score = mean * (1.0 - qcv);
+            }
+            out[v] = (float)score;
+        }
+    }
+}
+
+// Refinement of the marked per-direction values of a (X, Y, Z, 72) output: thread per value.
+template <typename SrcT>
+__global__ void __launch_bounds__(256)
+lne3d_refine_dirs_kernel(const SrcT *__restrict__ vol, int Xs, int Ys, int Zs, int src_off, int X, int Y, int Z,
+                         const unsigned long long *__restrict__ maxkey, float *__restrict__ out) {
+    __shared__ signed char tab[L3_T * L3_P * 3];
+    for (int i = threadIdx.x; i < L3_T * L3_P * 3; i += 256) tab[i] = (signed char)c_baked3d.v[i];
+    __syncthreads();
+    const int64_t n = (int64_t)X * Y * Z * L3_T;
+    const double eps = 1e-8 * (maxkey ? fabs(double_of_key(*maxkey)) : 1.0);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        if (out[i] != L3Q_SENTINEL) continue;
+        const int t = (int)(i % L3_T);
+        const int64_t v = i / L3_T;
+        const int z = (int)(v % Z);
+        const int64_t rest = v / Z;
+        const int y = (int)(rest % Y), x = (int)(rest / Y);
+        out[i] = (float)l3_line_value_f64<SrcT, HIPR_FLAVOUR_ME2>(vol, Xs, Ys, Zs, x - L3_HALF + src_off, y - L3_HALF + src_off,
+                                                                 z - L3_HALF + src_off, tab, t, eps);
     }
 }
 
@@ -362,19 +663,42 @@ static int lne3d_dispatch(const T *vol, int Xs, int Ys, int Zs, int padded, int 
     return after_launch();
 }
 
+// strict relative parity is on unless HIPR_LNE3D_REFINE=0 (2 = diagnostic: mark only)
+static int refine3d_mode() {
+    static const int mode = [] {
+        const char *e = getenv("HIPR_LNE3D_REFINE");
+        return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1;
+    }();
+    return mode;
+}
+
 template <typename SrcT, int FLAVOUR, int MODE>
 static int launch_q3d(const SrcT *vol, int Xs, int Ys, int Zs, int src_off, int X, int Y, int Z,
                       const unsigned long long *maxkey, float *out, cudaStream_t st) {
     constexpr int TX = 8;
     constexpr int SX = TX + L3_P - 1;
     const size_t smem = (size_t)SX * L3_SY * L3_SZ * sizeof(float);
-    auto kern = lne3d_q_kernel<SrcT, FLAVOUR, MODE, TX>;
+    const int mode = refine3d_mode();
+    auto kern = mode ? lne3d_q_kernel<SrcT, FLAVOUR, MODE, TX, true> : lne3d_q_kernel<SrcT, FLAVOUR, MODE, TX, false>;
     static std::atomic<uint64_t> attr_done{0};
-    if (first_use_on_device(attr_done)) HIPR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (first_use_on_device(attr_done)) {
+        HIPR_CUDA(cudaFuncSetAttribute(lne3d_q_kernel<SrcT, FLAVOUR, MODE, TX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        HIPR_CUDA(cudaFuncSetAttribute(lne3d_q_kernel<SrcT, FLAVOUR, MODE, TX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
     const int nzb = (Z + L3_TZ - 1) / L3_TZ, nyb = (Y + L3_TY - 1) / L3_TY, nxb = (X + TX - 1) / TX;
     if ((int64_t)nzb * nyb > 0x7fffffffLL || nxb > 65535) return HIPR_E_RANGE;
     dim3 grid((unsigned)(nzb * nyb), (unsigned)nxb);
     kern<<<grid, 256, smem, st>>>(vol, Xs, Ys, Zs, src_off, X, Y, Z, maxkey, out);
+    int e = after_launch();
+    if (e || mode != 1) return e;
+    const int64_t nvox = (int64_t)X * Y * Z;
+    if (MODE == 0) {
+        lne3d_refine_dirs_kernel<SrcT><<<sm_count() * 8, 256, 0, st>>>(vol, Xs, Ys, Zs, src_off, X, Y, Z, maxkey, out);
+    } else {
+        const int64_t nb = (nvox + RF3_SPAN - 1) / RF3_SPAN;
+        if (nb > 0x7fffffffLL) return HIPR_E_RANGE;
+        lne3d_refine_kernel<SrcT, FLAVOUR><<<(unsigned)nb, RF3_THREADS, 0, st>>>(vol, Xs, Ys, Zs, src_off, X, Y, Z, maxkey, out);
+    }
     return after_launch();
 }
 

@@ -97,6 +97,15 @@ __device__ __forceinline__ T quartile_sorted(const T (&v)[N]) {
     return (rem >= 2) ? (b - d * ((T)1 - t)) : (a + d * t);
 }
 
+// The same lerp from the two order statistics around the virtual index (N = 72: ranks 17 / 18 and 53 / 54).
+template <typename T, int NUM>
+__device__ __forceinline__ T quartile_pair(T a, T b) {
+    constexpr int rem = (NUM * (72 - 1)) % 4;
+    const T t = (T)rem * (T)0.25;
+    const T d = b - a;
+    return (rem >= 2) ? (b - d * ((T)1 - t)) : (a + d * t);
+}
+
 // Reduction over the N directions -> one score.
 template <typename T, int N, int FLAVOUR>
 __device__ __forceinline__ T reduce_dirs(T (&r)[N]) {

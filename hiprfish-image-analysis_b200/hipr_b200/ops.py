@@ -474,10 +474,26 @@ def lne3d_fixed(volume, flavour="ME2", patch_size=11, theta_range=9, phi_range=9
 def neighbor3d_score(cube, flavour="ME2", patch_size=11, theta_range=9, phi_range=9, dtype=None):
     """cube (X, Y, Z, C) float32 -> score volume (X, Y, Z): channel sum -> /max -> edge pad ->
     3-D line profiles -> epilogue (bio/...analysis.py:807-817 for 'ME2').  dtype=None: float64 sums +
-    fixed-point stencil (float32 score); torch.float32 / float64: floating-point stencil of that type."""
+    fixed-point stencil (float32 score); torch.float32 / float64: floating-point stencil of that type.
+    A batch (N, X, Y, Z, C) of independent z-stacks alternates between two streams, so that the channel sum of
+    stack i+1 (HBM-bound) runs beside the stencil of stack i (ALU-bound); returns (N, X, Y, Z)."""
     cube = _dev(cube, "cube", (torch.float32,))
+    if cube.dim() == 5:
+        cur = torch.cuda.current_stream(cube.device)
+        side = _side_streams(cube.device)
+        for st in side:
+            st.wait_stream(cur)
+        res = []
+        for i, c in enumerate(cube):
+            with torch.cuda.stream(side[i % len(side)]):
+                res.append(neighbor3d_score(c, flavour, patch_size, theta_range, phi_range, dtype))
+        for st in side:
+            cur.wait_stream(st)
+        for r in res:
+            r.record_stream(cur)
+        return torch.stack(res)
     if cube.dim() != 4:
-        raise ValueError("cube must be (X, Y, Z, C)")
+        raise ValueError("cube must be (X, Y, Z, C) or (N, X, Y, Z, C)")
     s, mk = channel_sum(cube, None, normalize=False, dtype=dtype or torch.float64, return_max=True)
     if dtype is None:
         res = lne3d_fixed(s, flavour, patch_size, theta_range, phi_range, padded=False, maxkey=mk)

@@ -157,3 +157,35 @@ def test_neighbor3d_host_entry_point(torch_cuda, oracle, flavour):
     np.testing.assert_allclose(got, want, rtol=1e-5, atol=5e-7)
     with pytest.raises(ValueError):
         hipr_b200.neighbor3d_score_host(cube[0], flavour)
+
+
+@pytest.mark.parametrize("flavour", ["ME2", "F2", "F3"])
+def test_score3d_strict_relative_parity(torch_cuda, oracle, flavour):
+    """1e-5 RELATIVE, no absolute term (north_star's gate as written), on a z-stack cube through the default
+    fixed-point pipeline: voxels the grid cannot resolve are recomputed in float64 (lne3d_refine_kernel); a batch of
+    two stacks (two streams) gives the same volumes."""
+    import hipr_b200
+    from hipr_b200 import synth
+    cube = synth.make_volume_cube(24, 20, 40, 95, seed=11)
+    cube = cube + 0.01 * torch_cuda.rand((24, 20, 40, 1), generator=torch_cuda.Generator().manual_seed(3))
+    s = cube.numpy().astype(np.float64).sum(axis=3)
+    want = oracle.lne3d(s / s.max(), flavour)
+    got = hipr_b200.neighbor3d_score(cube.cuda(), flavour)
+    assert bool((got >= 0).all() | torch_cuda.isnan(got).any()), "a refinement sentinel survived"
+    np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-5, atol=0, equal_nan=True)
+    both = hipr_b200.neighbor3d_score(torch_cuda.stack([cube, cube * 0.5]).cuda(), flavour)
+    assert torch_cuda.equal(both[0], got)
+    np.testing.assert_allclose(both[1].cpu().numpy(), want, rtol=1e-5, atol=0, equal_nan=True)
+
+
+def test_dirs3d_strict_relative_parity(torch_cuda, oracle):
+    """line_profile_memory_efficient_v2's (X, Y, Z, 72) output from the fixed-point stencil: every value within 1e-5
+    relative (values the grid cannot resolve are recomputed in float64, lne3d_refine_dirs_kernel)."""
+    import hipr_b200
+    vol = smooth_image((14, 13, 38), 33).astype(np.float64) + 0.05
+    vol /= vol.max()
+    vp = np.pad(vol, 5, mode="edge")
+    got = hipr_b200.lne3d_fixed(_cuda(torch_cuda, vp), "ME2", padded=True, dirs_only=True).cpu().numpy()
+    want = oracle.line_profile_memory_efficient_v2(vp, 11, 9, 9)
+    assert (got >= 0).all()
+    np.testing.assert_allclose(got, want, rtol=1e-5, atol=0)
