@@ -550,6 +550,35 @@ def run_b200(args):
         cell_tab = ops.cell_spectra_host(host, labels_host)
     cell_e2e_ms = 1e3 * (time.perf_counter() - t0) / cell_e2e_steps
     cell_e2e_n = int(cell_tab[0].size)
+    # the scripts' real flow (syn/..._measurement.py:161-173): score map, (watershed on the host), per-cell spectra of the
+    # SAME cube: one upload through the handle API instead of two
+    with ops.Fov(host) as fov:
+        fov.score("F1", out=score_host)
+        fov.cell_spectra(labels_host)
+    barrier()
+    flow_steps = 5
+    t0 = time.perf_counter()
+    for _ in range(flow_steps):
+        with ops.Fov(host) as fov:
+            fov.score("F1", out=score_host)
+            flow_tab = fov.cell_spectra(labels_host)
+    flow_ms = 1e3 * (time.perf_counter() - t0) / flow_steps
+    flow_equal = bool(np.array_equal(score_host, host_api_score) and np.array_equal(flow_tab[0], cell_tab[0])
+                      and np.array_equal(flow_tab[1], cell_tab[1]) and np.allclose(flow_tab[2], cell_tab[2], rtol=1e-12, atol=0))
+    # plain host-to-device ceiling: the same number of bytes from page-locked memory with one cudaMemcpyAsync, every
+    # rank at once (what the box's PCIe / host memory system delivers to N GPUs simultaneously)
+    pin = torch.empty(H * W * C, dtype=torch.float32).pin_memory()
+    dst = torch.empty(H * W * C, dtype=torch.float32, device=dev)
+    dst.copy_(pin, non_blocking=True)
+    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    h0.record()
+    for _ in range(5):
+        dst.copy_(pin, non_blocking=True)
+    h1.record()
+    barrier()
+    h2d_ms = h0.elapsed_time(h1) / 5
+    del pin, dst
     # the same FOV as the uint16 counts a detector delivers (value = count / 65535 in float32, bioformats' rescale)
     raw = ops.pinned_empty((H, W, C), np.uint16)
     cmax = float(cubes[0].max())
@@ -565,12 +594,12 @@ def run_b200(args):
     del raw
 
     # ---- reduce over ranks (max time) -----------------------------------------------------------
-    t = torch.tensor([ms, cell_ms, e2e_dev_ms, e2e_wall_ms, k1_ms, raw_dev_ms, cell_e2e_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, cell_ms, e2e_dev_ms, e2e_wall_ms, k1_ms, raw_dev_ms, cell_e2e_ms, flow_ms, h2d_ms], dtype=torch.float64, device=dev)
     cnt = torch.tensor([launches, cells_per_step], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    ms, cell_ms, e2e_dev_ms, e2e_wall_ms, k1_ms, raw_dev_ms, cell_e2e_ms = [float(x) for x in t.tolist()]
+    ms, cell_ms, e2e_dev_ms, e2e_wall_ms, k1_ms, raw_dev_ms, cell_e2e_ms, flow_ms, h2d_ms = [float(x) for x in t.tolist()]
     launches, cells_all = int(cnt[0].item()), float(cnt[1].item())
 
     # ---- the other configurations, recorded in the same line -----------------------------------
@@ -612,7 +641,16 @@ def run_b200(args):
                     "h2d_bytes_per_step": npix * C * 4, "d2h_bytes_per_step": npix * 4, "steps": e2e_steps,
                     "ms_per_step": e2e_dev_ms / e2e_steps, "wall_ms_per_step": e2e_wall_ms / e2e_steps,
                     "api": "hipr_neighbor2d_host (C ABI, pinned host buffers)", "score_mean": score_check,
-                    "host_numa_binding": numa},
+                    "host_numa_binding": numa,
+                    "h2d_ceiling": {"gb_s_per_gpu": npix * C * 4 / (h2d_ms * 1e-3) / 1e9, "ms": h2d_ms,
+                                    "how": "plain cudaMemcpyAsync of the same %d bytes from page-locked memory, all %d ranks at once, "
+                                           "max over ranks" % (npix * C * 4, world)},
+                    "frac_of_h2d_ceiling": h2d_ms / (e2e_dev_ms / e2e_steps)},
+            "e2e_flow": {"ms_per_fov": flow_ms, "mpix_per_s": world * npix / (flow_ms * 1e-3) / 1e6,
+                         "api": "hipr_fov_upload -> hipr_fov_score -> hipr_fov_cell_spectra -> hipr_fov_release: ONE upload of the "
+                                "cube for the score map and the per-cell spectra (wall clock, incl. device allocation)",
+                         "two_uploads_ms": e2e_dev_ms / e2e_steps + cell_e2e_ms, "equals_separate_calls": flow_equal,
+                         "h2d_bytes_per_fov": npix * C * 4 + npix * labels[0].element_size()},
             "e2e_raw_u16": {"value": world * npix * e2e_steps / (raw_dev_ms * 1e-3) / 1e6, "unit": "Mpix/s",
                             "h2d_bytes_per_step": npix * C * 2, "d2h_bytes_per_step": npix * 4,
                             "ms_per_step": raw_dev_ms / e2e_steps,

@@ -36,7 +36,38 @@ struct Workspace {
     int last_C = 0;
     bool ready = false;
 };
-static Workspace g_ws;
+// One workspace per device: its streams, events and buffers belong to the device that was current when they were
+// created, so a process that drives several GPUs (or switches devices between calls) never shares them.
+constexpr int kMaxDevices = 32;
+static Workspace g_ws_dev[kMaxDevices];
+static Workspace *ws_current() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return nullptr;
+    return &g_ws_dev[dev];
+}
+static thread_local float t_last_ms = -1.f;      // hipr_host_last_elapsed_ms: the calling thread's last host call
+
+// An error return after the first enqueue must not leave copies from the caller's buffers (or into them) in flight:
+// the caller may free them.  Unless dismissed, the guard drains both streams on scope exit.
+struct DrainOnError {
+    Workspace &w;
+    bool armed = true;
+    explicit DrainOnError(Workspace &ws) : w(ws) {}
+    void dismiss() { armed = false; }
+    ~DrainOnError() {
+        if (!armed) return;
+        if (w.copy) cudaStreamSynchronize(w.copy);
+        if (w.comp) cudaStreamSynchronize(w.comp);
+    }
+};
+
+// host threads that copy a pageable array into the page-locked staging ring (HIPR_HOST_COPY_THREADS overrides)
+static int host_copy_threads() {
+    int n = (int)std::thread::hardware_concurrency();
+    n = n > 8 ? 8 : n;                                      // measured with 8: 143 -> 48 ms per 1.59 GB cube
+    if (const char *ev = getenv("HIPR_HOST_COPY_THREADS")) n = atoi(ev);
+    return n > 16 ? 16 : (n < 1 ? 1 : n);
+}
 
 static int ws_init(Workspace &w) {
     if (w.ready) return HIPR_OK;
@@ -167,7 +198,9 @@ extern "C" int hipr_host_free(void *ptr) {
     return HIPR_OK;
 }
 extern "C" int hipr_host_release_workspace(void) {
-    Workspace &w = g_ws;
+    Workspace *wp = ws_current();
+    if (!wp) return HIPR_E_NODEVICE;
+    Workspace &w = *wp;
     std::lock_guard<std::mutex> lock(w.mu);
     cudaDeviceSynchronize();
     for (int i = 0; i < NBUF; ++i) {
@@ -194,10 +227,13 @@ static int neighbor2d_host_impl(const void *cube_host, int sample_bytes, float s
                                 int patch_size, int n_dirs, const int32_t *table_host, int flavour, float *score_host,
                                 float *sum_host, double denoise_h = 0.0) {
     if (!cube_host || !score_host || H < 1 || W < 1 || C < 1) return HIPR_E_ARG;
-    Workspace &w = g_ws;
+    Workspace *wp = ws_current();
+    if (!wp) return HIPR_E_NODEVICE;
+    Workspace &w = *wp;
     std::lock_guard<std::mutex> lock(w.mu);
     int e = ws_init(w);
     if (e) return e;
+    DrainOnError guard(w);
     const int64_t row_bytes = (int64_t)W * C * sample_bytes;
     const int rows = band_rows(row_bytes, H);
     if ((e = ws_bands(w, (size_t)rows * row_bytes))) return e;
@@ -213,10 +249,7 @@ static int neighbor2d_host_impl(const void *cube_host, int sample_bytes, float s
     HIPR_CUDA(cudaMemsetAsync(key, 0x00, 8, w.comp));
     HIPR_CUDA(cudaMemsetAsync(key + 1, 0xff, 8, w.comp));
     const bool pageable = is_pageable(cube_host);
-    int copy_threads = (int)std::thread::hardware_concurrency();
-    copy_threads = copy_threads > 8 ? 8 : copy_threads;     // measured with 8: 143 -> 48 ms per 1.59 GB cube
-    if (const char *ev = getenv("HIPR_HOST_COPY_THREADS")) copy_threads = atoi(ev);
-    copy_threads = copy_threads > 16 ? 16 : (copy_threads < 1 ? 1 : copy_threads);
+    const int copy_threads = host_copy_threads();
     if (pageable && (e = ws_stage(w, (size_t)rows * row_bytes))) return e;
     int b = 0;
     for (int r0 = 0; r0 < H; r0 += rows, ++b) {
@@ -259,6 +292,8 @@ static int neighbor2d_host_impl(const void *cube_host, int sample_bytes, float s
         HIPR_CUDA(cudaEventRecord(w.t1, w.comp));
         HIPR_CUDA(cudaStreamSynchronize(w.comp));
         HIPR_CUDA(cudaEventElapsedTime(&w.last_ms, w.t0, w.t1));
+        t_last_ms = w.last_ms;
+        guard.dismiss();
         return HIPR_OK;
     }
     // fixed-point stencil for the (11, 9) table every pipeline uses; float64 kernel otherwise
@@ -284,6 +319,8 @@ static int neighbor2d_host_impl(const void *cube_host, int sample_bytes, float s
     HIPR_CUDA(cudaEventRecord(w.t1, w.comp));            // ... and stops after the last D2H
     HIPR_CUDA(cudaStreamSynchronize(w.comp));
     HIPR_CUDA(cudaEventElapsedTime(&w.last_ms, w.t0, w.t1));
+    t_last_ms = w.last_ms;
+    guard.dismiss();
     return HIPR_OK;
 }
 
@@ -298,10 +335,13 @@ extern "C" int hipr_neighbor2d_host(const float *cube_host, int H, int W, int C,
 extern "C" int hipr_neighbor3d_host(const float *cube_host, int X, int Y, int Z, int C, int patch_size, int n_dirs,
                                     const int32_t *table_host, int flavour, float *score_host) {
     if (!cube_host || !score_host || !table_host || X < 1 || Y < 1 || Z < 1 || C < 1) return HIPR_E_ARG;
-    Workspace &w = g_ws;
+    Workspace *wp = ws_current();
+    if (!wp) return HIPR_E_NODEVICE;
+    Workspace &w = *wp;
     std::lock_guard<std::mutex> lock(w.mu);
     int e = ws_init(w);
     if (e) return e;
+    DrainOnError guard(w);
     const int64_t plane_px = (int64_t)Y * Z, plane_bytes = plane_px * C * 4, nvox = (int64_t)X * plane_px;
     const int planes = band_rows(plane_bytes, X);
     if ((e = ws_bands(w, (size_t)planes * plane_bytes))) return e;
@@ -316,8 +356,7 @@ extern "C" int hipr_neighbor3d_host(const float *cube_host, int X, int Y, int Z,
     HIPR_CUDA(cudaMemsetAsync(key, 0x00, 8, w.comp));
     HIPR_CUDA(cudaMemsetAsync(key + 1, 0xff, 8, w.comp));
     const bool pageable = is_pageable(cube_host);
-    int copy_threads = (int)std::thread::hardware_concurrency();
-    copy_threads = copy_threads > 8 ? 8 : (copy_threads < 1 ? 1 : copy_threads);
+    const int copy_threads = host_copy_threads();
     if (pageable && (e = ws_stage(w, (size_t)planes * plane_bytes))) return e;
     int b = 0;
     for (int x0 = 0; x0 < X; x0 += planes, ++b) {
@@ -354,6 +393,8 @@ extern "C" int hipr_neighbor3d_host(const float *cube_host, int X, int Y, int Z,
     HIPR_CUDA(cudaEventRecord(w.t1, w.comp));
     HIPR_CUDA(cudaStreamSynchronize(w.comp));
     HIPR_CUDA(cudaEventElapsedTime(&w.last_ms, w.t0, w.t1));
+    t_last_ms = w.last_ms;
+    guard.dismiss();
     return HIPR_OK;
 }
 
@@ -375,7 +416,7 @@ extern "C" int hipr_neighbor2d_host_raw(const void *cube_host, int sample_bytes,
                                 score_host, sum_host);
 }
 
-extern "C" double hipr_host_last_elapsed_ms(void) { return (double)g_ws.last_ms; }
+extern "C" double hipr_host_last_elapsed_ms(void) { return (double)t_last_ms; }
 
 extern "C" int hipr_cell_spectra_host(const float *cube_host, const void *labels_host, int label_bytes, int64_t npix,
                                       int64_t row_len, int C, int64_t capacity, int64_t *n_cells, int64_t *labels_out,
@@ -384,10 +425,13 @@ extern "C" int hipr_cell_spectra_host(const float *cube_host, const void *labels
         npix < 1 || C < 1 || capacity < 0)
         return HIPR_E_ARG;
     if (label_bytes != 4 && label_bytes != 8) return HIPR_E_DTYPE;
-    Workspace &w = g_ws;
+    Workspace *wp = ws_current();
+    if (!wp) return HIPR_E_NODEVICE;
+    Workspace &w = *wp;
     std::lock_guard<std::mutex> lock(w.mu);
     int e = ws_init(w);
     if (e) return e;
+    DrainOnError guard(w);
     // labels first (small), max label back to the host to size the accumulators
     if ((e = ws_aux(w, 3, (size_t)npix * label_bytes))) return e;
     if ((e = ws_aux(w, 2, 64))) return e;
@@ -399,7 +443,10 @@ extern "C" int hipr_cell_spectra_host(const float *cube_host, const void *labels
     HIPR_CUDA(cudaMemcpyAsync(&max_label, scalar_dev, 8, cudaMemcpyDeviceToHost, w.comp));
     HIPR_CUDA(cudaStreamSynchronize(w.comp));
     *n_cells = 0;
-    if (max_label <= 0) return HIPR_OK;
+    if (max_label <= 0) {
+        guard.dismiss();
+        return HIPR_OK;
+    }
     const size_t sums_bytes = (size_t)(max_label + 1) * C * 8;
     const size_t cnt_bytes = (size_t)(max_label + 1) * 4;
     if ((e = ws_aux(w, 4, sums_bytes + cnt_bytes + 16))) return e;
@@ -418,8 +465,7 @@ extern "C" int hipr_cell_spectra_host(const float *cube_host, const void *labels
     }
     if ((e = ws_bands(w, (size_t)band_px * px_bytes))) return e;
     const bool pageable = is_pageable(cube_host);
-    int copy_threads = (int)std::thread::hardware_concurrency();
-    copy_threads = copy_threads > 8 ? 8 : (copy_threads < 1 ? 1 : copy_threads);
+    const int copy_threads = host_copy_threads();
     if (pageable && (e = ws_stage(w, (size_t)band_px * px_bytes))) return e;
     int b = 0;
     for (int64_t p0 = 0; p0 < npix; p0 += band_px, ++b) {
@@ -462,20 +508,25 @@ extern "C" int hipr_cell_spectra_host(const float *cube_host, const void *labels
     w.last_cells = n;
     w.last_max_label = max_label;
     w.last_C = C;
-    if (n > capacity) return HIPR_E_RANGE;     // the table stays on the device: hipr_cell_spectra_host_fetch
-    if (n == 0) return HIPR_OK;
+    if (n > capacity || n == 0) {
+        guard.dismiss();                       // everything enqueued so far has completed
+        return n ? HIPR_E_RANGE : HIPR_OK;     // n > capacity: the table stays on the device (hipr_cell_spectra_host_fetch)
+    }
     HIPR_CUDA(cudaMemcpyAsync(labels_out, lab_dev, (size_t)n * 8, cudaMemcpyDeviceToHost, w.comp));
     HIPR_CUDA(cudaMemcpyAsync(area_out, area_dev, (size_t)n * 8, cudaMemcpyDeviceToHost, w.comp));
     HIPR_CUDA(cudaMemcpyAsync(avgint_out, avg_dev, (size_t)n * row_bytes, cudaMemcpyDeviceToHost, w.comp));
     HIPR_CUDA(cudaMemcpyAsync(avgint_norm_out, norm_dev, (size_t)n * row_bytes, cudaMemcpyDeviceToHost, w.comp));
     HIPR_CUDA(cudaStreamSynchronize(w.comp));
+    guard.dismiss();
     return HIPR_OK;
 }
 
 extern "C" int hipr_cell_spectra_host_fetch(int64_t capacity, int64_t *labels_out, int64_t *area_out, double *avgint_out,
                                             double *avgint_norm_out) {
     if (!labels_out || !area_out || !avgint_out || !avgint_norm_out) return HIPR_E_ARG;
-    Workspace &w = g_ws;
+    Workspace *wp = ws_current();
+    if (!wp) return HIPR_E_NODEVICE;
+    Workspace &w = *wp;
     std::lock_guard<std::mutex> lock(w.mu);
     if (w.last_cells < 0 || !w.aux[5]) return HIPR_E_ARG;      // no table to fetch
     const int64_t n = w.last_cells, max_label = w.last_max_label;
@@ -492,5 +543,254 @@ extern "C" int hipr_cell_spectra_host_fetch(int64_t capacity, int64_t *labels_ou
     HIPR_CUDA(cudaMemcpyAsync(avgint_out, avg_dev, (size_t)n * row_bytes, cudaMemcpyDeviceToHost, w.comp));
     HIPR_CUDA(cudaMemcpyAsync(avgint_norm_out, norm_dev, (size_t)n * row_bytes, cudaMemcpyDeviceToHost, w.comp));
     HIPR_CUDA(cudaStreamSynchronize(w.comp));
+    return HIPR_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Field-of-view handle: ONE upload of the cube for the score map and the per-cell spectra.
+// The scripts hold `image_registered` across both steps (syn/..._measurement.py:161-173: generate_2d_segmentation
+// returns it, the regionprops loop reads it again after the watershed); with the two host entry points above the
+// cube crosses PCIe twice (29 + 32 ms per 2048^2 FOV).  hipr_fov_upload streams it to the device once, in row bands
+// under the channel sum, and keeps cube, sums and range resident; hipr_fov_score and hipr_fov_cell_spectra then cost
+// a stencil / a label upload + one pass over the resident cube.
+// ---------------------------------------------------------------------------------------------------------------
+namespace hipr {
+struct Fov {
+    int device = 0, H = 0, W = 0, C = 0;
+    float *cube = nullptr;
+    double *sum = nullptr;
+    float *score = nullptr;            // (H, W) float32 scratch: score, then the normalised sum
+    unsigned long long *keys = nullptr;
+    void *labels = nullptr;            // grown on demand
+    size_t labels_bytes = 0;
+    void *cells = nullptr;             // accumulators + compacted table
+    size_t cells_bytes = 0;
+    cudaStream_t copy = nullptr, comp = nullptr;
+    cudaEvent_t copied = nullptr, t0 = nullptr, t1 = nullptr;
+    float last_ms = -1.f;
+    std::mutex mu;
+};
+struct DeviceScope {                   // run on the handle's device, restore the caller's afterwards
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceScope(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) ok = (cudaSetDevice(dev) == cudaSuccess);
+    }
+    ~DeviceScope() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+static void fov_free(Fov *f) {
+    if (!f) return;
+    if (f->comp) cudaStreamSynchronize(f->comp);
+    if (f->copy) cudaStreamSynchronize(f->copy);
+    cudaFree(f->cube);
+    cudaFree(f->sum);
+    cudaFree(f->score);
+    cudaFree(f->keys);
+    cudaFree(f->labels);
+    cudaFree(f->cells);
+    if (f->copied) cudaEventDestroy(f->copied);
+    if (f->t0) cudaEventDestroy(f->t0);
+    if (f->t1) cudaEventDestroy(f->t1);
+    if (f->copy) cudaStreamDestroy(f->copy);
+    if (f->comp) cudaStreamDestroy(f->comp);
+    delete f;
+}
+}  // namespace hipr
+
+extern "C" int hipr_fov_upload(const float *cube_host, int H, int W, int C, void **handle_out) {
+    if (!cube_host || !handle_out || H < 1 || W < 1 || C < 1) return HIPR_E_ARG;
+    *handle_out = nullptr;
+    Fov *f = new Fov;
+    if (cudaGetDevice(&f->device) != cudaSuccess) {
+        delete f;
+        return HIPR_E_NODEVICE;
+    }
+    f->H = H; f->W = W; f->C = C;
+    const size_t npix = (size_t)H * W;
+    int e = HIPR_OK;
+    auto fail = [&](int code) {
+        fov_free(f);
+        return code;
+    };
+#define HIPR_FOV(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return fail((int)_e); } while (0)
+    HIPR_FOV(cudaMalloc((void **)&f->cube, npix * C * sizeof(float)));
+    HIPR_FOV(cudaMalloc((void **)&f->sum, npix * sizeof(double)));
+    HIPR_FOV(cudaMalloc((void **)&f->score, npix * sizeof(float)));
+    HIPR_FOV(cudaMalloc((void **)&f->keys, 64));
+    HIPR_FOV(cudaStreamCreateWithFlags(&f->copy, cudaStreamNonBlocking));
+    HIPR_FOV(cudaStreamCreateWithFlags(&f->comp, cudaStreamNonBlocking));
+    HIPR_FOV(cudaEventCreateWithFlags(&f->copied, cudaEventDisableTiming));
+    HIPR_FOV(cudaEventCreate(&f->t0));
+    HIPR_FOV(cudaEventCreate(&f->t1));
+    HIPR_FOV(cudaEventRecord(f->t0, f->copy));
+    HIPR_FOV(cudaStreamWaitEvent(f->comp, f->t0, 0));
+    HIPR_FOV(cudaMemsetAsync(f->keys, 0x00, 8, f->comp));
+    HIPR_FOV(cudaMemsetAsync(f->keys + 1, 0xff, 8, f->comp));
+    // bands of ~32 MiB straight into the resident cube; the channel sum of band b runs under the copy of band b + 1.
+    // Page-locked memory (hipr_host_alloc) goes at the PCIe rate; pageable memory is staged by the driver.
+    const int64_t row_bytes = (int64_t)W * C * 4;
+    const int rows = band_rows(row_bytes, H);
+    for (int r0 = 0; r0 < H; r0 += rows) {
+        const int nr = (H - r0 < rows) ? H - r0 : rows;
+        float *dst = f->cube + (size_t)r0 * W * C;
+        HIPR_FOV(cudaMemcpyAsync(dst, (const char *)cube_host + (int64_t)r0 * row_bytes, (size_t)nr * row_bytes,
+                                 cudaMemcpyHostToDevice, f->copy));
+        HIPR_FOV(cudaEventRecord(f->copied, f->copy));
+        HIPR_FOV(cudaStreamWaitEvent(f->comp, f->copied, 0));
+        if ((e = chansum_band(dst, 4, 1.f, (int64_t)nr * W, C, f->sum + (size_t)r0 * W, f->keys, f->comp))) return fail(e);
+    }
+    HIPR_FOV(cudaEventRecord(f->t1, f->comp));
+    HIPR_FOV(cudaStreamSynchronize(f->comp));      // the caller may reuse cube_host
+    HIPR_FOV(cudaEventElapsedTime(&f->last_ms, f->t0, f->t1));
+#undef HIPR_FOV
+    t_last_ms = f->last_ms;
+    *handle_out = f;
+    return HIPR_OK;
+}
+
+extern "C" int hipr_fov_release(void *handle) {
+    Fov *f = reinterpret_cast<Fov *>(handle);
+    if (!f) return HIPR_OK;
+    DeviceScope scope(f->device);
+    fov_free(f);
+    return HIPR_OK;
+}
+
+// device pointers of a handle's resident arrays (for callers that continue on the device): cube (H, W, C) float32,
+// channel sums (H, W) float64, range keys (2 uint64)
+extern "C" int hipr_fov_device_arrays(void *handle, const float **cube_dev, const double **sum_dev, const uint64_t **range_dev) {
+    Fov *f = reinterpret_cast<Fov *>(handle);
+    if (!f) return HIPR_E_ARG;
+    if (cube_dev) *cube_dev = f->cube;
+    if (sum_dev) *sum_dev = f->sum;
+    if (range_dev) *range_dev = reinterpret_cast<const uint64_t *>(f->keys);
+    return HIPR_OK;
+}
+
+extern "C" int hipr_fov_score(void *handle, int patch_size, int n_dirs, const int32_t *table_host, int flavour,
+                              float *score_host, float *sum_host) {
+    Fov *f = reinterpret_cast<Fov *>(handle);
+    if (!f || !score_host || !table_host) return HIPR_E_ARG;
+    std::lock_guard<std::mutex> lock(f->mu);
+    DeviceScope scope(f->device);
+    if (!scope.ok) return HIPR_E_NODEVICE;
+    const int H = f->H, W = f->W;
+    const size_t img_bytes = (size_t)H * W * 4;
+    struct Drain {
+        cudaStream_t s;
+        bool armed = true;
+        ~Drain() { if (armed) cudaStreamSynchronize(s); }
+    } drain{f->comp};
+    HIPR_CUDA(cudaEventRecord(f->t0, f->comp));
+    const bool tile_local = (flavour == HIPR_FLAVOUR_F1 || flavour == HIPR_FLAVOUR_F2);
+    int e = hipr_lne2d_q(f->sum, H, W, W, 0, HIPR_F64, patch_size, n_dirs, table_host, flavour,
+                         tile_local ? nullptr : reinterpret_cast<const uint64_t *>(f->keys), f->score, f->comp);
+    if (e == HIPR_E_TABLE && !(patch_size == 11 && n_dirs == 9)) {
+        // general parameters: float64 stencil into scratch, then cast
+        double *score64 = nullptr;
+        HIPR_CUDA(cudaMallocAsync((void **)&score64, (size_t)H * W * 8, f->comp));
+        e = hipr_lne2d(f->sum, H, W, W, 0, HIPR_F64, patch_size, n_dirs, table_host, flavour,
+                       reinterpret_cast<const uint64_t *>(f->keys), score64, f->comp);
+        if (!e) e = hipr_normalize_cast(score64, (int64_t)H * W, nullptr, f->score, f->comp);
+        cudaFreeAsync(score64, f->comp);
+    }
+    if (e) return e;
+    HIPR_CUDA(cudaMemcpyAsync(score_host, f->score, img_bytes, cudaMemcpyDeviceToHost, f->comp));
+    if (sum_host) {
+        if ((e = hipr_normalize_cast(f->sum, (int64_t)H * W, reinterpret_cast<const uint64_t *>(f->keys), f->score, f->comp)))
+            return e;
+        HIPR_CUDA(cudaMemcpyAsync(sum_host, f->score, img_bytes, cudaMemcpyDeviceToHost, f->comp));
+    }
+    HIPR_CUDA(cudaEventRecord(f->t1, f->comp));
+    HIPR_CUDA(cudaStreamSynchronize(f->comp));
+    drain.armed = false;
+    HIPR_CUDA(cudaEventElapsedTime(&f->last_ms, f->t0, f->t1));
+    t_last_ms = f->last_ms;
+    return HIPR_OK;
+}
+
+extern "C" int hipr_fov_cell_spectra(void *handle, const void *labels_host, int label_bytes, int64_t capacity,
+                                     int64_t *n_cells, int64_t *labels_out, int64_t *area_out, double *avgint_out,
+                                     double *avgint_norm_out) {
+    Fov *f = reinterpret_cast<Fov *>(handle);
+    if (!f || !labels_host || !n_cells || !labels_out || !area_out || !avgint_out || !avgint_norm_out || capacity < 0)
+        return HIPR_E_ARG;
+    if (label_bytes != 4 && label_bytes != 8) return HIPR_E_DTYPE;
+    std::lock_guard<std::mutex> lock(f->mu);
+    DeviceScope scope(f->device);
+    if (!scope.ok) return HIPR_E_NODEVICE;
+    const int64_t npix = (int64_t)f->H * f->W;
+    const int C = f->C;
+    struct Drain {
+        cudaStream_t s;
+        bool armed = true;
+        ~Drain() { if (armed) cudaStreamSynchronize(s); }
+    } drain{f->comp};
+    if ((size_t)npix * label_bytes > f->labels_bytes) {
+        cudaFree(f->labels);
+        f->labels = nullptr;
+        f->labels_bytes = 0;
+        HIPR_CUDA(cudaMalloc(&f->labels, (size_t)npix * label_bytes));
+        f->labels_bytes = (size_t)npix * label_bytes;
+    }
+    HIPR_CUDA(cudaEventRecord(f->t0, f->comp));
+    HIPR_CUDA(cudaMemcpyAsync(f->labels, labels_host, (size_t)npix * label_bytes, cudaMemcpyHostToDevice, f->comp));
+    int64_t *scalar_dev = reinterpret_cast<int64_t *>(f->keys + 4);      // the handle's 64-byte scratch, past the keys
+    int e = hipr_label_max(f->labels, label_bytes, npix, scalar_dev, f->comp);
+    if (e) return e;
+    int64_t max_label = 0;
+    HIPR_CUDA(cudaMemcpyAsync(&max_label, scalar_dev, 8, cudaMemcpyDeviceToHost, f->comp));
+    HIPR_CUDA(cudaStreamSynchronize(f->comp));
+    *n_cells = 0;
+    if (max_label <= 0) {
+        drain.armed = false;
+        return HIPR_OK;
+    }
+    const size_t row_bytes = (size_t)C * 8;
+    const size_t sums_bytes = (size_t)(max_label + 1) * row_bytes, cnt_bytes = ((size_t)(max_label + 1) * 4 + 15) & ~(size_t)15;
+    const size_t fin_off = sums_bytes + cnt_bytes + 16;
+    const size_t need = fin_off + 16 + (size_t)max_label * (16 + 2 * row_bytes);
+    if (need > f->cells_bytes) {
+        cudaFree(f->cells);
+        f->cells = nullptr;
+        f->cells_bytes = 0;
+        HIPR_CUDA(cudaMalloc(&f->cells, need));
+        f->cells_bytes = need;
+    }
+    double *sums = reinterpret_cast<double *>(f->cells);
+    int32_t *counts = reinterpret_cast<int32_t *>((char *)f->cells + sums_bytes);
+    char *fin = (char *)f->cells + fin_off;
+    int32_t *n_dev = reinterpret_cast<int32_t *>(fin);
+    int64_t *lab_dev = reinterpret_cast<int64_t *>(fin + 16);
+    int64_t *area_dev = lab_dev + max_label;
+    double *avg_dev = reinterpret_cast<double *>(area_dev + max_label);
+    double *norm_dev = avg_dev + (size_t)max_label * C;
+    HIPR_CUDA(cudaMemsetAsync(f->cells, 0, fin_off, f->comp));
+    if ((e = hipr_cell_spectra_accumulate(f->cube, f->labels, label_bytes, npix, f->W, C, max_label, sums, counts, nullptr,
+                                          f->comp)))
+        return e;
+    if ((e = hipr_cell_spectra_finalize(sums, counts, max_label, C, n_dev, lab_dev, area_dev, avg_dev, norm_dev, f->comp)))
+        return e;
+    int32_t n = 0;
+    HIPR_CUDA(cudaMemcpyAsync(&n, n_dev, 4, cudaMemcpyDeviceToHost, f->comp));
+    HIPR_CUDA(cudaStreamSynchronize(f->comp));
+    *n_cells = n;
+    if (n > capacity || n == 0) {
+        drain.armed = false;
+        return n ? HIPR_E_RANGE : HIPR_OK;    // HIPR_E_RANGE: call again with capacity >= *n_cells (the cube is resident)
+    }
+    HIPR_CUDA(cudaMemcpyAsync(labels_out, lab_dev, (size_t)n * 8, cudaMemcpyDeviceToHost, f->comp));
+    HIPR_CUDA(cudaMemcpyAsync(area_out, area_dev, (size_t)n * 8, cudaMemcpyDeviceToHost, f->comp));
+    HIPR_CUDA(cudaMemcpyAsync(avgint_out, avg_dev, (size_t)n * row_bytes, cudaMemcpyDeviceToHost, f->comp));
+    HIPR_CUDA(cudaMemcpyAsync(avgint_norm_out, norm_dev, (size_t)n * row_bytes, cudaMemcpyDeviceToHost, f->comp));
+    HIPR_CUDA(cudaEventRecord(f->t1, f->comp));
+    HIPR_CUDA(cudaStreamSynchronize(f->comp));
+    drain.armed = false;
+    HIPR_CUDA(cudaEventElapsedTime(&f->last_ms, f->t0, f->t1));
+    t_last_ms = f->last_ms;
     return HIPR_OK;
 }

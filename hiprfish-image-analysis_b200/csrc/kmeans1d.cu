@@ -2,7 +2,7 @@
 //   KMeans(n_clusters = k, random_state = 0).fit_predict(image.reshape(-1, 1))
 // as the measurement scripts call it on image_final, the denoised sum and their logarithms
 // (syn/..._measurement.py:125-149; bio/..._analysis.py:367-392, 463-486, 819-846; eco/..._measurement.py:73-85),
-// with scikit-learn 1.9.0 (installed here) as the pinned oracle: k-means++ seeding driven by the caller's
+// with scikit-learn 1.9.0 (installed here) as the pinned reference of the parity tests: k-means++ seeding driven by the caller's
 // uniform random numbers (numpy RandomState(seed) on the host, in the order scikit-learn consumes them), Lloyd
 // iterations with scikit-learn's two stopping rules (labels unchanged; squared centre shift <= tol * var(x)),
 // labels from the final centres, best of n_init by inertia.

@@ -61,6 +61,11 @@ _SIGNATURES = {
     "hipr_neighbor2d_host_raw": (_i, [_vp, _i, C.c_double, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp]),
     "hipr_cell_spectra_host": (_i, [_vp, _vp, _i, _i64, _i64, _i, _i64, _vp, _vp, _vp, _vp, _vp]),
     "hipr_cell_spectra_host_fetch": (_i, [_i64, _vp, _vp, _vp, _vp]),
+    "hipr_fov_upload": (_i, [_vp, _i, _i, _i, C.POINTER(_vp)]),
+    "hipr_fov_score": (_i, [_vp, _i, _i, _vp, _i, _vp, _vp]),
+    "hipr_fov_cell_spectra": (_i, [_vp, _vp, _i, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "hipr_fov_device_arrays": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
+    "hipr_fov_release": (_i, [_vp]),
     "hipr_host_last_elapsed_ms": (C.c_double, []),
     "hipr_host_alloc": (_i, [C.POINTER(_vp), _i64]),
     "hipr_host_free": (_i, [_vp]),

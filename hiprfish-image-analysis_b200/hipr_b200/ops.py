@@ -805,3 +805,87 @@ def cell_spectra_host(cube, labels):
     check(code, "cell_spectra_host")
     k = int(n.value)
     return lab[:k], area[:k], avg[:k], norm[:k]
+
+
+class Fov:
+    """One upload of a field of view for both steps of `measure_biofilm_images_no_reference`
+    (syn/...measurement.py:161-173): the (H, W, C) float32 numpy cube is streamed to the current CUDA device once and
+    stays resident; `score()` is lines 105-124 (without the denoise), `cell_spectra(segmentation)` lines 167-172.
+
+        with hipr_b200.Fov(image_registered) as fov:
+            image_final = fov.score("F1")
+            ...                                  # watershed on the host
+            labels, area, avgint, avgint_norm = fov.cell_spectra(image_seg)
+    """
+
+    def __init__(self, cube):
+        cube = np.ascontiguousarray(cube)
+        if cube.dtype != np.float32:
+            raise TypeError("cube must be float32, got %s" % cube.dtype)
+        if cube.ndim != 3:
+            raise ValueError("cube must be (H, W, C)")
+        self.shape = cube.shape
+        h = C.c_void_p()
+        check(lib().hipr_fov_upload(cube.ctypes.data_as(C.c_void_p), cube.shape[0], cube.shape[1], cube.shape[2],
+                                    C.byref(h)), "fov_upload")
+        self._h = h
+
+    def _handle(self):
+        if self._h is None:
+            raise ValueError("this field of view has been released")
+        return self._h
+
+    def score(self, flavour="F1", patch_size=11, phi_range=9, return_sum=False, out=None):
+        H, W, _ = self.shape
+        tab = tables.line_table_2d(patch_size, phi_range)
+        score = out if out is not None else np.empty((H, W), dtype=np.float32)
+        s = np.empty((H, W), dtype=np.float32) if return_sum else None
+        check(lib().hipr_fov_score(self._handle(), tab.shape[1], tab.shape[0], _tab_ptr(tab), _flavour(flavour),
+                                   score.ctypes.data_as(C.c_void_p), s.ctypes.data_as(C.c_void_p) if return_sum else None),
+              "fov_score")
+        return (score, s) if return_sum else score
+
+    def cell_spectra(self, labels):
+        labels = np.ascontiguousarray(labels)
+        if labels.dtype not in (np.int32, np.int64):
+            raise TypeError("labels must be int32 or int64, got %s" % labels.dtype)
+        H, W, Cn = self.shape
+        if labels.shape != (H, W):
+            raise ValueError("labels must be (%d, %d)" % (H, W))
+        cap = 4096
+        while True:
+            lab, area = np.empty(cap, np.int64), np.empty(cap, np.int64)
+            avg, norm = np.empty((cap, Cn), np.float64), np.empty((cap, Cn), np.float64)
+            n = C.c_int64(0)
+            code = lib().hipr_fov_cell_spectra(self._handle(), labels.ctypes.data_as(C.c_void_p), labels.itemsize, cap,
+                                               C.byref(n), lab.ctypes.data_as(C.c_void_p), area.ctypes.data_as(C.c_void_p),
+                                               avg.ctypes.data_as(C.c_void_p), norm.ctypes.data_as(C.c_void_p))
+            if code == -7 and n.value > cap:
+                cap = int(n.value)           # the cube is resident: the second call is one pass over it, no upload
+                continue
+            check(code, "fov_cell_spectra")
+            k = int(n.value)
+            return lab[:k], area[:k], avg[:k], norm[:k]
+
+    def device_arrays(self):
+        """(cube, channel sums, range keys) device pointers as ints, for callers that continue on the device."""
+        a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        check(lib().hipr_fov_device_arrays(self._handle(), C.byref(a), C.byref(b), C.byref(c)), "fov_device_arrays")
+        return a.value, b.value, c.value
+
+    def close(self):
+        if self._h is not None:
+            lib().hipr_fov_release(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

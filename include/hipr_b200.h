@@ -395,8 +395,28 @@ int hipr_cell_spectra_host(const float *cube_host, const void *labels_host, int 
  * device, into arrays of sufficient capacity without recomputing it. */
 int hipr_cell_spectra_host_fetch(int64_t capacity, int64_t *labels_out, int64_t *area_out, double *avgint_out,
                                  double *avgint_norm_out);
-/* device-clock duration (CUDA events: before the first H2D .. after the last D2H) of the most
- * recent hipr_neighbor2d_host call in this process, in ms; negative if none yet */
+/* ---- field-of-view handle: one upload for the score map AND the per-cell spectra ------------------------------
+ * The scripts hold `image_registered` across both steps (syn/..._measurement.py:161-173: generate_2d_segmentation
+ * returns it, the regionprops loop at :167-172 reads it again after the watershed).  hipr_fov_upload streams the
+ * (H, W, C) float32 cube to the CURRENT device once (row bands under the channel sum; page-locked memory from
+ * hipr_host_alloc goes at the PCIe rate) and keeps cube, float64 channel sums and their range resident:
+ *   hipr_fov_score         = hipr_neighbor2d_host without the upload (score_host / sum_host as there)
+ *   hipr_fov_cell_spectra  = hipr_cell_spectra_host without the upload (HIPR_E_RANGE with *n_cells set when
+ *                            capacity is too small: call again, the cube is still resident)
+ *   hipr_fov_device_arrays   device pointers of the resident cube / sums / range keys (any may be NULL)
+ *   hipr_fov_release         frees everything
+ * A handle belongs to the device it was created on; calls switch to that device and restore the caller's.  Calls on
+ * one handle are serialised; different handles are independent (own streams). */
+int hipr_fov_upload(const float *cube_host, int H, int W, int C, void **handle_out);
+int hipr_fov_score(void *handle, int patch_size, int n_dirs, const int32_t *table_host, int flavour,
+                   float *score_host, float *sum_host);
+int hipr_fov_cell_spectra(void *handle, const void *labels_host, int label_bytes, int64_t capacity, int64_t *n_cells,
+                          int64_t *labels_out, int64_t *area_out, double *avgint_out, double *avgint_norm_out);
+int hipr_fov_device_arrays(void *handle, const float **cube_dev, const double **sum_dev, const uint64_t **range_dev);
+int hipr_fov_release(void *handle);
+
+/* device-clock duration (CUDA events: before the first H2D .. after the last D2H) of the calling thread's most
+ * recent host-buffer or handle call, in ms; negative if none yet */
 double hipr_host_last_elapsed_ms(void);
 int hipr_host_alloc(void **ptr, int64_t bytes);   /* page-locked host memory */
 int hipr_host_free(void *ptr);

@@ -404,3 +404,41 @@ def test_score_strict_relative_parity(torch_cuda, oracle, flavour):
         assert (got >= 0).all(), "a refinement sentinel survived"
         np.testing.assert_allclose(got, want, rtol=1e-5, atol=0)
         assert np.array_equal(got == 0, want == 0)
+
+
+def test_fov_handle_one_upload_for_score_and_spectra(torch_cuda, oracle):
+    """hipr_fov_*: the cube is uploaded once; score and per-cell spectra equal the two host entry points bit for bit
+    and the oracle within the gates; int64 labels, more cells than the first capacity guess, release."""
+    import hipr_b200
+    from hipr_b200 import synth
+    cube, labels, _ = synth.make_fov(200, 176, 95, fov_index=8, drop_fraction=0.1)
+    cube_np, lab_np = cube.numpy(), labels.numpy()
+    with hipr_b200.Fov(cube_np) as fov:
+        for fl in ("F1", "F2", "F3"):
+            got = fov.score(fl)
+            assert np.array_equal(got, hipr_b200.neighbor2d_score_host(cube_np, fl))
+            np.testing.assert_allclose(got, oracle.neighbor2d_score(cube_np, fl), rtol=1e-5, atol=0)
+        score, s = fov.score("F1", return_sum=True)
+        want_s = cube_np.astype(np.float64).sum(axis=2)
+        np.testing.assert_allclose(s, want_s / want_s.max(), rtol=1e-6)
+        for lab_in in (lab_np, lab_np.astype(np.int64)):
+            l1, a1, v1, n1 = fov.cell_spectra(lab_in)
+            l2, a2, v2, n2 = hipr_b200.cell_spectra_host(cube_np, lab_in)
+            assert np.array_equal(l1, l2) and np.array_equal(a1, a2)
+            np.testing.assert_allclose(v1, v2, rtol=1e-12)
+            wl, wa, wavg, wnorm = oracle.cell_spectra(lab_in, cube_np)
+            assert np.array_equal(l1, wl) and np.array_equal(a1, wa)
+            np.testing.assert_allclose(v1, wavg, rtol=1e-5)
+            np.testing.assert_allclose(n1, wnorm, rtol=1e-5)
+        general = fov.score("F1", patch_size=7, phi_range=5)          # outside the fixed-point fast path
+        np.testing.assert_allclose(general, oracle.lne2d(want_s / want_s.max(), "F1", 7, 5), rtol=1e-5, atol=1e-6)
+        assert all(p for p in fov.device_arrays())
+    with pytest.raises(ValueError):
+        fov.score("F1")                                               # released
+    many = np.arange(1, 200 * 176 + 1, dtype=np.int32).reshape(200, 176)    # 35,200 one-pixel cells > first capacity
+    with hipr_b200.Fov(cube_np) as fov:
+        l, a, v, _ = fov.cell_spectra(many)
+        assert l.size == many.size and (a == 1).all()
+        np.testing.assert_allclose(v, cube_np.reshape(-1, 95).astype(np.float64), rtol=1e-12)
+    with pytest.raises(TypeError):
+        hipr_b200.Fov(cube_np.astype(np.float64))
