@@ -119,6 +119,135 @@ cell_accumulate_kernel(const float *__restrict__ cube, const LabelT *__restrict_
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Bulk-copy variant (opt-in, HIPR_CELL_BULK=1; measured SLOWER than the load variant above on B200: 0.173 vs
+// 0.112 ms on the 25 %-foreground synthetic FOV, 0.370 vs 0.275 ms = 4.3 vs 5.8 TB/s on a 98 %-foreground label
+// image -- with two 12 KB stages per warp only 8 warps fit an SM, and their per-pixel shared-memory walk is
+// latency-bound; kept as the starting point for a 16-pixel-group / more-warps version): the same run-length
+// accumulation, but the channel vectors come
+// through the TMA engine instead of per-lane loads.  Foreground pixels of a 32-pixel group are contiguous bytes of
+// the cube (a pixel is 4 C bytes), so ONE 1-D bulk copy (cp.async.bulk, SASS UBLKCP) fetches the span from the
+// group's first to its last foreground pixel -- rounded out to 16-byte boundaries -- into a shared-memory stage that
+// belongs to the warp; background-only groups are never fetched.  Every warp runs its own two-stage pipeline (own
+// mbarriers, no CTA-wide synchronisation): it issues the copies of groups k + 1 and k + 2 before it consumes group
+// k, lane = channel straight out of shared memory (consecutive lanes, consecutive words: no bank conflicts).  Bytes in
+// flight cost no registers: 8 warps x 2 stages x 12 KB = 195 KB per SM against ~55 KB for the load variant, which
+// is what an HBM-bound gather needs (the load variant reached 3.6 TB/s on the bytes it fetched).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int CBK_STAGES = 2;
+
+template <typename LabelT, int CK>
+__global__ void __launch_bounds__(256, 1)
+cell_accumulate_bulk_kernel(const float *__restrict__ cube, const LabelT *__restrict__ labels, int64_t npix, int C,
+                            int64_t max_label, int stage_bytes, double *__restrict__ sums, int *__restrict__ counts,
+                            int *__restrict__ overflow) {
+    extern __shared__ __align__(128) unsigned char cbk_smem[];
+    __shared__ __align__(8) uint64_t bars[8 * CBK_STAGES];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    unsigned char *my_stage = cbk_smem + (size_t)warp * CBK_STAGES * stage_bytes;
+    uint64_t *my_bar = bars + warp * CBK_STAGES;
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < CBK_STAGES; ++s) mbar_init(&my_bar[s], 1);
+        fence_barrier_init();
+    }
+    __syncwarp();
+    const uint64_t policy = policy_evict_first();
+    const int64_t warp0 = (int64_t)blockIdx.x * nw + warp;
+    const int64_t nwarps = (int64_t)gridDim.x * nw;
+    const int64_t ngroups = (npix + 31) >> 5;
+    const int64_t px_bytes = (int64_t)C * 4;
+    const unsigned char *cube_b = reinterpret_cast<const unsigned char *>(cube);
+    bool chan_ok[CK];
+#pragma unroll
+    for (int j = 0; j < CK; ++j) chan_ok[j] = (lane + 32 * j) < C;
+
+    long long lab_s[CBK_STAGES];
+    unsigned fg_s[CBK_STAGES];
+    int off_s[CBK_STAGES];          // byte offset of the group's FIRST foreground pixel inside the stage
+    unsigned par_s[CBK_STAGES];
+#pragma unroll
+    for (int s = 0; s < CBK_STAGES; ++s) { lab_s[s] = 0; fg_s[s] = 0; off_s[s] = 0; par_s[s] = 0; }
+
+    auto issue = [&](int64_t grp, int s) {
+        long long lab = 0;
+        if (grp < ngroups && (grp << 5) + lane < npix) lab = (long long)labels[(grp << 5) + lane];
+        if (lab > max_label) {
+            if (overflow) atomicAdd(overflow, 1);
+            lab = 0;
+        }
+        const unsigned fg = __ballot_sync(0xffffffffu, lab > 0);
+        lab_s[s] = lab;
+        fg_s[s] = fg;
+        if (fg == 0) return;
+        const int first = __ffs(fg) - 1, last = 31 - __clz(fg);
+        const int64_t b0 = ((grp << 5) + first) * px_bytes, b1 = ((grp << 5) + last + 1) * px_bytes;
+        const int64_t a0 = b0 & ~(int64_t)15, a1 = (b1 + 15) & ~(int64_t)15;
+        off_s[s] = (int)(b0 - a0);
+        if (lane == 0) {
+            mbar_expect_tx(&my_bar[s], (uint32_t)(a1 - a0));
+            bulk_g2s(my_stage + (size_t)s * stage_bytes, cube_b + a0, (uint32_t)(a1 - a0), &my_bar[s], policy);
+        }
+    };
+    auto consume = [&](int s) {
+        unsigned fg = fg_s[s];
+        if (fg == 0) return;
+        mbar_wait(&my_bar[s], par_s[s]);
+        par_s[s] ^= 1u;
+        const int first = __ffs(fg) - 1;
+        const float *base = reinterpret_cast<const float *>(my_stage + (size_t)s * stage_bytes + off_s[s]) + lane;
+        const long long lab = lab_s[s];
+        long long cur = -1;
+        int run = 0;
+        float acc[CK];
+#pragma unroll
+        for (int j = 0; j < CK; ++j) acc[j] = 0.f;
+        while (fg) {
+            const int q = __ffs(fg) - 1;
+            fg &= fg - 1;
+            const long long ql = __shfl_sync(0xffffffffu, lab, q);
+            const float *px = base + (q - first) * C;
+            float v[CK];
+#pragma unroll
+            for (int j = 0; j < CK; ++j) v[j] = chan_ok[j] ? px[32 * j] : 0.f;
+            if (ql != cur) {
+                if (run > 0) {
+#pragma unroll
+                    for (int j = 0; j < CK; ++j)
+                        if (chan_ok[j]) atomicAdd(&sums[cur * C + lane + 32 * j], (double)acc[j]);
+                    if (lane == 0) atomicAdd(&counts[cur], run);
+                }
+                cur = ql;
+                run = 0;
+#pragma unroll
+                for (int j = 0; j < CK; ++j) acc[j] = 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < CK; ++j) acc[j] += v[j];
+            ++run;
+        }
+        if (run > 0) {
+#pragma unroll
+            for (int j = 0; j < CK; ++j)
+                if (chan_ok[j]) atomicAdd(&sums[cur * C + lane + 32 * j], (double)acc[j]);
+            if (lane == 0) atomicAdd(&counts[cur], run);
+        }
+        __syncwarp();          // every lane has read the stage before lane 0 refills it
+    };
+
+    // prologue: the first CBK_STAGES groups of this warp are in flight before anything is consumed
+#pragma unroll
+    for (int s = 0; s < CBK_STAGES; ++s) issue(warp0 + s * nwarps, s);
+    for (int64_t grp = warp0; grp < ngroups; grp += CBK_STAGES * nwarps) {
+#pragma unroll
+        for (int s = 0; s < CBK_STAGES; ++s) {
+            if (grp + s * nwarps >= ngroups) break;
+            consume(s);
+            issue(grp + (s + CBK_STAGES) * nwarps, s);
+        }
+    }
+}
+
 template <typename LabelT>
 __global__ void __launch_bounds__(256)
 label_max_kernel(const LabelT *__restrict__ labels, int64_t npix, unsigned long long *__restrict__ out) {
@@ -213,6 +342,32 @@ static int accumulate_launch(const float *cube, const LabelT *labels, int64_t np
                              int64_t max_label, double *sums, int *counts, int *overflow, cudaStream_t st) {
     (void)row_len;   // reserved: the run-length kernel treats the label image as a flat array
     const int64_t ngroups = (npix + 31) / 32;
+    // bulk-copy variant: needs spans that can be rounded out to 16 bytes inside the cube
+    static const bool bulk_on = [] { const char *e = getenv("HIPR_CELL_BULK"); return e && e[0] == '1'; }();
+    if (bulk_on && C <= 128 && (((uintptr_t)cube) & 15) == 0 && (npix * (int64_t)C) % 4 == 0) {
+        const int stage_bytes = (32 * C * 4 + 16 + 127) / 128 * 128;
+        int warps = 8;
+        while (warps > 1 && (size_t)warps * CBK_STAGES * stage_bytes > 200 * 1024) --warps;
+        const size_t smem = (size_t)warps * CBK_STAGES * stage_bytes;
+        int64_t blocks = sm_count();
+        if (blocks > (ngroups + warps - 1) / warps) blocks = (ngroups + warps - 1) / warps;
+        const int ck = (C + 31) / 32;
+#define HIPR_CELL_BULK_LAUNCH(CKV)                                                                                  \
+    do {                                                                                                            \
+        auto kern = cell_accumulate_bulk_kernel<LabelT, CKV>;                                                       \
+        static std::atomic<uint64_t> attr_done{0};                                                                  \
+        if (first_use_on_device(attr_done)) HIPR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
+        kern<<<(unsigned)blocks, warps * 32, smem, st>>>(cube, labels, npix, C, max_label, stage_bytes, sums, counts, overflow); \
+    } while (0)
+        switch (ck) {
+            case 1: HIPR_CELL_BULK_LAUNCH(1); break;
+            case 2: HIPR_CELL_BULK_LAUNCH(2); break;
+            case 3: HIPR_CELL_BULK_LAUNCH(3); break;
+            default: HIPR_CELL_BULK_LAUNCH(4); break;
+        }
+#undef HIPR_CELL_BULK_LAUNCH
+        return after_launch();
+    }
     for (int c_base = 0; c_base < C; c_base += 128) {
         const int rem = C - c_base;
         const int ck = rem >= 97 ? 4 : (rem + 31) / 32;
