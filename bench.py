@@ -640,9 +640,16 @@ def run_b200(args):
     if rank == 0:
         value = world * npix * args.steps / (ms * 1e-3) / 1e6
         k1_gbs = npix * BYTES_PER_PIXEL / (k1_ms * 1e-3) / 1e9
-        traffic = None
+        traffic, traffic_src = None, None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))["chansum_bytes_per_launch"]
+            import hashlib
+            tj = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+            traffic = tj["chansum_bytes_per_launch"]
+            sha = hashlib.sha256(open(os.path.join(PKG, "csrc", "chansum.cu"), "rb").read()).hexdigest()
+            traffic_src = {"capture": tj.get("source"), "round": tj.get("round"),
+                           "how": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel "
+                                  "(profiles/), not re-measured in this run",
+                           "kernel_source_unchanged_since_capture": tj.get("chansum_cu_sha256") == sha}
         except Exception:
             pass
         line = {
@@ -659,10 +666,10 @@ def run_b200(args):
                          "share_of_serial_step": k1_ms / (ms / args.steps) if args.streams == 1 else None,
                          "share_of_step": min(1.0, k1_ms / (ms / args.steps)),
                          "share_note": "two streams: the stencil of FOV i runs under the channel sum of FOV i+1, so the step is "
-                                       "~one channel sum; ncu's serialised launch list gives 0.77 (profiles/r01_summary.md), "
-                                       "--streams 1 gives 0.74" if args.streams > 1 else "streams=1: serial step",
+                                       "~one channel sum; ncu's serialised launch list and --streams 1 give the serial share "
+                                       "(profiles/r02_summary.md)" if args.streams > 1 else "streams=1: serial step",
                          "achieved": k1_gbs, "peak": hbm_peak,
-                         "unit": "GB/s", "frac": k1_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": k1_gbs / hbm_peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": npix * BYTES_PER_PIXEL, "ms_per_launch": k1_ms},
             "e2e": {"value": world * npix * e2e_steps / (e2e_dev_ms * 1e-3) / 1e6, "unit": "Mpix/s",
                     "h2d_bytes_per_step": npix * C * 4, "d2h_bytes_per_step": npix * 4, "steps": e2e_steps,

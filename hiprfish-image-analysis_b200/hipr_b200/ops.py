@@ -606,6 +606,20 @@ def cell_geometry(labels, max_label=None):
     return lab[:n], area[:n], geom[:n]
 
 
+def orientation_xy(geometry):
+    """Orientation column in the 'xy' coordinate convention of scikit-image <= 0.15 (regionprops' default before
+    0.16, the era the reference's cpython-35 artefacts point to): -0.5 * atan2(2 mu11, var_col - var_row), from the
+    central moments cell_geometry returns (columns mu20 = row variance, mu02 = column variance, mu11).  cell_geometry's
+    own `orientation` column follows the 'rc' convention of scikit-image >= 0.16.  Neither is pinned by the reference
+    (no version file, scikit-image not installed here): PARITY UNPINNED, see INTEGRATION.md.  geometry: the (n, 9)
+    table (torch tensor or numpy array) -> (n,) of the same kind."""
+    if isinstance(geometry, torch.Tensor):
+        mu20, mu02, mu11 = geometry[:, 6], geometry[:, 7], geometry[:, 8]
+        return -0.5 * torch.atan2(2.0 * mu11, mu02 - mu20)
+    g = np.asarray(geometry)
+    return -0.5 * np.arctan2(2.0 * g[:, 8], g[:, 7] - g[:, 6])
+
+
 def paint_labels(labels, values, max_label=None):
     """out[p] = values[labels[p]]: the `image[segmentation == label] = value` loops of
     eco/hiprfish_imaging_image_classification.py:64-70 / bio/...analysis.py:1247-1257 as one gather.

@@ -95,8 +95,11 @@ def main():
           and not r["kernel"].split("chansum_bulk_kernel<")[1].split(",")[1:2] in (["1"], [" 1"], [" 1>"], [" (bool)1"])]
     if k1:
         tr = [r["dram__bytes_read.sum [byte]"] + r["dram__bytes_write.sum [byte]"] for r in k1]
+        import hashlib
+        src = os.path.join(os.path.dirname(HERE), "hiprfish-image-analysis_b200", "csrc", "chansum.cu")
         js = {"chansum_bytes_per_launch": sum(tr) / len(tr), "launches": len(tr), "source": k1[0]["report"],
-              "workload": "2048x2048x95 float32 cube (1,593,835,520 B) -> float64 sum image", "round": tag}
+              "workload": "2048x2048x95 float32 cube (1,593,835,520 B) -> float64 sum image", "round": tag,
+              "chansum_cu_sha256": hashlib.sha256(open(src, "rb").read()).hexdigest()}
         with open(os.path.join(HERE, "roofline_traffic.json"), "w") as f:
             json.dump(js, f, indent=1)
         print("roofline_traffic.json", js)
