@@ -28,14 +28,21 @@ def build(force=False, verbose=False, ptxas_verbose=False):
     build_dir = os.path.join(HERE, "build")
     os.makedirs(build_dir, exist_ok=True)
     procs = []
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))] + \
+              [os.path.join(INCLUDE, "hipr_b200.h"), os.path.abspath(__file__)]
+    newest_header = max(os.path.getmtime(h) for h in headers)
     for src in SOURCES:
         obj = os.path.join(build_dir, src.replace(".cu", ".o"))
+        objs.append(obj)
+        # per-object incremental build: an object is reused when it is newer than its source and every header
+        if not force and os.path.exists(obj) and \
+                os.path.getmtime(obj) > max(newest_header, os.path.getmtime(os.path.join(CSRC, src))):
+            continue
         cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if ptxas_verbose else []) + \
               ["-I", INCLUDE, "-I", CSRC, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             print(" ".join(cmd), flush=True)
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-        objs.append(obj)
     failed = False
     for src, p in procs:
         out, _ = p.communicate()
