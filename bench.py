@@ -308,6 +308,29 @@ def measure_next_rows(cube, labels, with_cpu):
     out["e2e_chain_with_denoise"] = {"ms": 1e3 * (time.perf_counter() - t0) / 3, "mpix_s": npix / ((time.perf_counter() - t0) / 3) / 1e6,
                                      "api": "hipr_neighbor2d_host_denoise (pinned host cube -> score, lines 105-124 in full)"}
     del host
+    # a1, the strict drop-in: the literal (H, W, 9, 11) float64 gather of line_profile_2d_v2 (792 B written + 8 read per
+    # pixel).  Device-resident against the HBM write roofline, and numpy -> numpy through hipr_line_profile_2d_host
+    # (3.3 GB of output per 2048^2 image: the call is the PCIe time of the result)
+    pad64 = torch.nn.functional.pad(s64[None, None], (5, 5, 5, 5), mode="replicate")[0, 0].contiguous()
+    t = gpu_ms(lambda: ops.line_profile_2d(pad64, 11, 9), n=5)
+    out["dropin_line_profile_2d_v2"] = {"ms": t, "gb_s": npix * 800 / t / 1e6, "bytes_per_px": 800}
+    pad_np = pad64.cpu().numpy()
+    lp_host = ops.line_profile_2d_host(pad_np, 11, 9, pinned=True)
+    t0 = time.perf_counter()
+    for _ in range(2):
+        ops.line_profile_2d_host(pad_np, 11, 9, out=lp_host)
+    t = 1e3 * (time.perf_counter() - t0) / 2
+    out["dropin_line_profile_2d_v2"].update({"host_ms_pinned_out": t, "host_gb_s": lp_host.nbytes / t / 1e6,
+                                             "api": "hipr_line_profile_2d_host (numpy float64 in, page-locked float64 out)"})
+    del lp_host, pad64
+    if with_cpu:
+        lp_page = np.empty((cube.shape[0], cube.shape[1], 9, 11), dtype=np.float64)
+        lp_page.fill(0.0)                                      # fault the pages in outside the timed call
+        t0 = time.perf_counter()
+        ops.line_profile_2d_host(pad_np, 11, 9, out=lp_page)
+        out["dropin_line_profile_2d_v2"]["host_ms_pageable_out"] = 1e3 * (time.perf_counter() - t0)
+        del lp_page
+    del pad_np
     score = ops.neighbor2d_pipeline(cube, "F1")[0]
     t = gpu_ms(lambda: ops.kmeans_threshold(score, 2), n=5)
     km = ops.kmeans_threshold(score, 2)

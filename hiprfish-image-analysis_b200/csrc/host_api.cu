@@ -15,6 +15,10 @@ std::atomic<int64_t> g_launches{0};
 
 int chansum_band(const void *cube, int sample_bytes, float scale, int64_t npix, int C, double *out,
                  unsigned long long *maxkey, cudaStream_t st);
+template <typename T>
+int gather_launch(const T *src, int64_t stride_a, int64_t stride_b, int inner, int64_t nrows, int rowlen, int K,
+                  const int *offs, T *out, cudaStream_t st);
+int check_table(const int32_t *table, int n_dirs, int P, int ndim);
 
 constexpr int NBUF = 3;
 struct Workspace {
@@ -329,6 +333,83 @@ static int neighbor2d_host_impl(const void *cube_host, int sample_bytes, float s
 extern "C" int hipr_neighbor2d_host(const float *cube_host, int H, int W, int C, int patch_size, int n_dirs,
                                     const int32_t *table_host, int flavour, float *score_host, float *sum_host) {
     return neighbor2d_host_impl(cube_host, 4, 1.f, H, W, C, patch_size, n_dirs, table_host, flavour, score_host, sum_host);
+}
+
+// The strict drop-in of line_profile_2d_v2 (eco/neighbor2d.pyx:8-64) from and to HOST arrays: padded float64 image in,
+// the literal (H, W, n_dirs, P) float64 gather out -- 792 B per pixel at (11, 9), 3.3 GB for a 2048^2 image, so the
+// call is the PCIe time of the OUTPUT.  The image is uploaded once; the gather runs in row bands of ~32 MiB of output
+// into three device buffers on the compute stream while the previous bands cross PCIe on the copy stream, straight
+// into out_host when it is page-locked, otherwise through the page-locked staging ring and a few host threads (a
+// direct device -> pageable copy is staged by the driver at ~11 GB/s).
+extern "C" int hipr_line_profile_2d_host(const double *image_padded_host, int Hp, int Wp, int patch_size, int n_dirs,
+                                         const int32_t *table_host, double *out_host) {
+    if (!image_padded_host || !out_host) return HIPR_E_ARG;
+    int e = check_table(table_host, n_dirs, patch_size, 2);
+    if (e) return e;
+    const int P = patch_size, H = Hp - (P - 1), W = Wp - (P - 1), K = n_dirs * P;
+    if (H < 1 || W < 1) return HIPR_E_PATCH;
+    int lin[HIPR_MAX_TABLE];
+    for (int i = 0; i < K; ++i) {
+        const int dy = table_host[2 * i], dx = table_host[2 * i + 1];
+        if (dy < 0 || dy >= P || dx < 0 || dx >= P) return HIPR_E_TABLE;
+        lin[i] = dy * Wp + dx;
+    }
+    Workspace *wp = ws_current();
+    if (!wp) return HIPR_E_NODEVICE;
+    Workspace &w = *wp;
+    std::lock_guard<std::mutex> lock(w.mu);
+    if ((e = ws_init(w))) return e;
+    DrainOnError guard(w);
+    const int64_t row_bytes = (int64_t)W * K * sizeof(double);
+    const int rows = band_rows(row_bytes, H);
+    if ((e = ws_bands(w, (size_t)rows * row_bytes))) return e;
+    if ((e = ws_aux(w, 0, (size_t)Hp * Wp * sizeof(double)))) return e;
+    double *img_dev = (double *)w.aux[0];
+    const bool pageable = is_pageable(out_host);
+    const int copy_threads = host_copy_threads();
+    if (pageable && (e = ws_stage(w, (size_t)rows * row_bytes))) return e;
+    HIPR_CUDA(cudaEventRecord(w.t0, w.comp));
+    HIPR_CUDA(cudaMemcpyAsync(img_dev, image_padded_host, (size_t)Hp * Wp * sizeof(double), cudaMemcpyHostToDevice, w.comp));
+    struct Pending { int slot; int64_t off; size_t bytes; };
+    std::vector<Pending> pend;          // pageable: bands whose staged copy still has to reach out_host
+    size_t drained = 0;
+    auto drain = [&](size_t upto) -> int {
+        for (; drained < upto; ++drained) {
+            const Pending &q = pend[drained];
+            HIPR_CUDA(cudaEventSynchronize(w.staged_out[q.slot]));
+            parallel_copy((char *)out_host + q.off, w.stage[q.slot], q.bytes, copy_threads);
+        }
+        return HIPR_OK;
+    };
+    int b = 0;
+    for (int r0 = 0; r0 < H; r0 += rows, ++b) {
+        const int nr = (H - r0 < rows) ? H - r0 : rows;
+        const int slot = b % NBUF;
+        const size_t bytes = (size_t)nr * row_bytes;
+        if (b >= NBUF) HIPR_CUDA(cudaStreamWaitEvent(w.comp, w.freed[slot], 0));   // its previous band has left the device
+        if ((e = gather_launch<double>(img_dev + (int64_t)r0 * Wp, Wp, 0, 1, nr, W, K, lin, (double *)w.band[slot], w.comp)))
+            return e;
+        HIPR_CUDA(cudaEventRecord(w.copied[slot], w.comp));
+        HIPR_CUDA(cudaStreamWaitEvent(w.copy, w.copied[slot], 0));
+        if (pageable) {
+            // stage[slot] is free once the host has copied band b - NBUF out of it
+            if (b >= NBUF && (e = drain((size_t)(b - NBUF + 1)))) return e;
+            HIPR_CUDA(cudaMemcpyAsync(w.stage[slot], w.band[slot], bytes, cudaMemcpyDeviceToHost, w.copy));
+            HIPR_CUDA(cudaEventRecord(w.staged_out[slot], w.copy));
+            pend.push_back(Pending{slot, (int64_t)r0 * row_bytes, bytes});
+        } else {
+            HIPR_CUDA(cudaMemcpyAsync((char *)out_host + (int64_t)r0 * row_bytes, w.band[slot], bytes, cudaMemcpyDeviceToHost, w.copy));
+        }
+        HIPR_CUDA(cudaEventRecord(w.freed[slot], w.copy));
+    }
+    if (pageable && (e = drain(pend.size()))) return e;
+    HIPR_CUDA(cudaEventRecord(w.t1, w.copy));
+    HIPR_CUDA(cudaStreamSynchronize(w.copy));
+    HIPR_CUDA(cudaStreamSynchronize(w.comp));
+    HIPR_CUDA(cudaEventElapsedTime(&w.last_ms, w.t0, w.t1));
+    t_last_ms = w.last_ms;
+    guard.dismiss();
+    return HIPR_OK;
 }
 
 // 3-D: cube_host (X, Y, Z, C) float32 -> score_host (X, Y, Z) float32: channel sum -> /max -> edge pad -> 72 x 11 line

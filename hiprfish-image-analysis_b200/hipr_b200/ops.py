@@ -389,6 +389,31 @@ def line_profile_2d(image_padded, patch_size, phi_range):
     return out
 
 
+def line_profile_2d_host(image_padded, patch_size, phi_range, out=None, pinned=False):
+    """numpy float64 (Hp, Wp) -> numpy float64 (Hp-P+1, Wp-P+1, phi_range, P) through hipr_line_profile_2d_host: the
+    gather runs in row bands on the device under the device -> host copy of the previous bands.  out: a caller's
+    array (page-locked or not); pinned=True returns an array backed by page-locked memory (torch's caching host
+    allocator), which the copy reaches at the PCIe rate without the staging ring."""
+    a = np.ascontiguousarray(image_padded)
+    if a.dtype != np.float64:
+        raise TypeError("image_padded must be float64, got %s" % a.dtype)
+    if a.ndim != 2:
+        raise ValueError("Buffer has wrong number of dimensions (expected 2, got %d)" % a.ndim)
+    tab = tables.line_table_2d(patch_size, phi_range)
+    R, P = tab.shape[0], tab.shape[1]
+    Hp, Wp = a.shape
+    if Hp < P or Wp < P:
+        raise ValueError("image smaller than the patch")
+    shape = (Hp - P + 1, Wp - P + 1, R, P)
+    if out is None:
+        out = torch.empty(shape, dtype=torch.float64, pin_memory=True).numpy() if pinned else np.empty(shape, dtype=np.float64)
+    elif out.shape != shape or out.dtype != np.float64 or not out.flags.c_contiguous:
+        raise ValueError("out must be a C-contiguous float64 array of shape %s" % (shape,))
+    check(lib().hipr_line_profile_2d_host(a.ctypes.data_as(C.c_void_p), Hp, Wp, P, R, _tab_ptr(tab),
+                                          out.ctypes.data_as(C.c_void_p)), "line_profile_2d_host")
+    return out
+
+
 def _vol(volume, name):
     volume = _dev(volume, name)
     if volume.dim() != 3:

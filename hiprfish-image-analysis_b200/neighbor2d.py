@@ -4,7 +4,7 @@
 
 Same name, same positional signature, same array conventions as eco/neighbor2d.pyx:8-64:
 numpy float64 (Hp, Wp) in -> new numpy float64 (Hp-P+1, Wp-P+1, phi_range, P) out, computed by
-the sm_100a gather kernel (host<->device copies included).  A torch CUDA tensor (float32 or
+the sm_100a gather kernel in row bands under the device -> host copy (hipr_line_profile_2d_host).  A torch CUDA tensor (float32 or
 float64) is also accepted and then a CUDA tensor of the same dtype is returned without any
 host copy.  There is no CPU fallback.
 
@@ -41,5 +41,6 @@ def line_profile_2d_v2(image_padded, patch_size, phi_range):
     if isinstance(image_padded, torch.Tensor):
         return ops.line_profile_2d(image_padded, patch_size, phi_range)
     a = _as_double_2d(image_padded, 2)
-    dev = torch.from_numpy(np.ascontiguousarray(a)).cuda()
-    return ops.line_profile_2d(dev, patch_size, phi_range).cpu().numpy()
+    # host arrays: banded gather under the device -> host copy, through the page-locked staging ring
+    # (hipr_line_profile_2d_host); the result is an ordinary numpy array, as the reference's np.zeros is
+    return ops.line_profile_2d_host(a, patch_size, phi_range)

@@ -141,6 +141,17 @@ int hipr_line_profile_2d(const void *image_padded_dev, int Hp, int Wp, int dtype
                          int patch_size, int n_dirs, const int32_t *table_host,
                          void *out_dev, void *stream);
 
+/* The same gather from and to HOST arrays: what `from neighbor2d import line_profile_2d_v2`
+ * (syn/..._measurement.py:30, :110) binds when the caller holds numpy arrays.
+ *   image_padded_host (Hp, Wp) float64, C order
+ *   out_host          (Hp-P+1, Wp-P+1, n_dirs, P) float64 -- 792 B per pixel at (11, 9)
+ * The image is uploaded once; the gather runs in row bands on the device while the previous
+ * bands cross PCIe (straight into out_host when it is page-locked, through the library's
+ * page-locked staging ring and host threads when it is ordinary pageable memory).  Blocking;
+ * hipr_host_last_elapsed_ms() gives the device-side time. */
+int hipr_line_profile_2d_host(const double *image_padded_host, int Hp, int Wp, int patch_size,
+                              int n_dirs, const int32_t *table_host, double *out_host);
+
 /* ---- 2-D fused stencil + epilogue ("local neighbourhood enhancement") ---------------------
  * Replaces line_profile_2d_v2 (eco/neighbor2d.pyx:56-63) + the numpy epilogue of `flavour`
  * (F1 syn/..._measurement.py:111-124, F2 bio/..._analysis.py:671-683, F3 :1114-1125) and,

@@ -43,6 +43,26 @@ def test_line_profile_2d_f32_device(torch_cuda, oracle):
     assert np.array_equal(got, want)
 
 
+def test_line_profile_2d_host_bands_pinned_and_pageable(torch_cuda, oracle):
+    """hipr_line_profile_2d_host: several row bands (32 MiB of output each), pageable output through the staging ring,
+    page-locked output directly, a caller's `out`; all bit-identical to the oracle and to the device operator."""
+    import hipr_b200
+    a = np.random.default_rng(11).random((330, 610))
+    want = oracle.line_profile_2d_v2(a, 11, 9)                       # (320, 600, 9, 11): 152 MB = 5 bands
+    got = hipr_b200.line_profile_2d_host(a, 11, 9)
+    assert got.dtype == np.float64 and np.array_equal(got, want)
+    pinned = hipr_b200.line_profile_2d_host(a, 11, 9, pinned=True)
+    assert np.array_equal(pinned, want)
+    out = np.full(want.shape, -1.0)
+    assert hipr_b200.line_profile_2d_host(a, 11, 9, out=out) is out and np.array_equal(out, want)
+    dev = hipr_b200.line_profile_2d(_cuda(torch_cuda, a), 11, 9).cpu().numpy()
+    assert np.array_equal(dev, want)
+    with pytest.raises(ValueError):
+        hipr_b200.line_profile_2d_host(a, 11, 9, out=np.empty((3, 3)))
+    with pytest.raises(TypeError):
+        hipr_b200.line_profile_2d_host(a.astype(np.float32), 11, 9)
+
+
 def test_line_profile_2d_noncontiguous_and_special_values(torch_cuda, oracle):
     import neighbor2d
     a = np.random.default_rng(4).random((60, 90))[::2, ::3]          # strided view, as a memoryview accepts
