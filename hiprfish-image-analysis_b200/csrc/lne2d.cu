@@ -167,6 +167,55 @@ gather_kernel(const T *__restrict__ src, int64_t stride_a, int64_t stride_b, int
     }
 }
 
+// 2-D form (K <= 128) at the write roofline: a CTA takes 64 consecutive pixels of a row and builds their whole
+// [64][K] output block in shared memory first -- warp w gathers sample k = w, w + 8, ... for 32 consecutive pixels per
+// instruction, so a load touches one or two lines (in the kernel above the 32 lanes of a load spread over the K
+// samples of two pixels, ~11 image rows: L1-tag bound, 3.8 TB/s) and the store lands at word p * K + k (K odd: no bank
+// conflicts) -- then streams the block out, contiguous, with 16-byte stores.
+constexpr int GT_PX = 64;
+template <typename T>
+__global__ void __launch_bounds__(GA_THREADS)
+gather_tile_kernel(const T *__restrict__ src, int64_t stride_row, int64_t nrows, int rowlen, int K,
+                   const __grid_constant__ Table2D offs, T *__restrict__ out) {
+    extern __shared__ __align__(16) unsigned char gt_smem[];
+    T *tile = reinterpret_cast<T *>(gt_smem);
+    int *s_off = reinterpret_cast<int *>(gt_smem + (size_t)GT_PX * K * sizeof(T));
+    for (int i = threadIdx.x; i < K; i += GA_THREADS) s_off[i] = offs.off[i];
+    __syncthreads();
+    const int chunks_per_row = (rowlen + GT_PX - 1) / GT_PX;
+    constexpr int VEC = 16 / sizeof(T);
+    for (int64_t w = blockIdx.x; w < nrows * chunks_per_row; w += gridDim.x) {
+        const int64_t row = w / chunks_per_row;
+        const int c0 = (int)(w - row * chunks_per_row) * GT_PX;
+        const int npx = min(GT_PX, rowlen - c0);
+        const T *sbase = src + row * stride_row + c0;
+        const int p = threadIdx.x & (GT_PX - 1);
+        if (p < npx) {
+            T *tp = tile + p * K;
+            const T *sp = sbase + p;
+            int k = threadIdx.x / GT_PX;
+            constexpr int KSTEP = GA_THREADS / GT_PX;
+            for (; k + 3 * KSTEP < K; k += 4 * KSTEP) {
+                const T v0 = sp[s_off[k]], v1 = sp[s_off[k + KSTEP]], v2 = sp[s_off[k + 2 * KSTEP]], v3 = sp[s_off[k + 3 * KSTEP]];
+                tp[k] = v0;
+                tp[k + KSTEP] = v1;
+                tp[k + 2 * KSTEP] = v2;
+                tp[k + 3 * KSTEP] = v3;
+            }
+            for (; k < K; k += KSTEP) tp[k] = sp[s_off[k]];
+        }
+        __syncthreads();
+        T *obase = out + (row * rowlen + c0) * (int64_t)K;
+        const int total = npx * K;
+        const int nvec = total / VEC;                      // obase is 16-byte aligned (checked by the launcher)
+        const int4 *t4 = reinterpret_cast<const int4 *>(tile);
+        int4 *o4 = reinterpret_cast<int4 *>(obase);
+        for (int v = threadIdx.x; v < nvec; v += GA_THREADS) __stcs(o4 + v, t4[v]);
+        for (int e = nvec * VEC + threadIdx.x; e < total; e += GA_THREADS) obase[e] = tile[e];
+        __syncthreads();
+    }
+}
+
 int check_table(const int32_t *table, int n_dirs, int P, int ndim) {
     if (!table) return HIPR_E_ARG;
     if (P < 3 || (P & 1) == 0 || P > HIPR_MAX_PATCH) return HIPR_E_PATCH;
@@ -220,6 +269,21 @@ int gather_launch(const T *src, int64_t stride_a, int64_t stride_b, int inner, i
     if (K < 1 || K > HIPR_MAX_TABLE) return HIPR_E_TABLE;
     Table2D offs;
     memcpy(offs.off, lin, K * sizeof(int));
+    // 2-D tables: the shared-memory block kernel, when every 64-pixel block of the output starts on 16 bytes
+    if (K <= 128 && inner == 1 && stride_b == 0 && (((uintptr_t)out) & 15u) == 0 &&
+        ((int64_t)rowlen * K * sizeof(T)) % 16 == 0 && ((int64_t)GT_PX * K * sizeof(T)) % 16 == 0) {
+        const size_t smem = (size_t)GT_PX * K * sizeof(T) + (size_t)K * sizeof(int);
+        static std::atomic<uint64_t> attr_gt{0};
+        if (first_use_on_device(attr_gt))
+            HIPR_CUDA(cudaFuncSetAttribute(gather_tile_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_PX * 128 * 8 + 128 * 4));
+        int per_sm = 1;
+        HIPR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gather_tile_kernel<T>, GA_THREADS, smem));
+        const int64_t work = nrows * ((rowlen + GT_PX - 1) / GT_PX);
+        int64_t grid = (int64_t)sm_count() * (per_sm < 1 ? 1 : per_sm);
+        if (grid > work) grid = work;
+        gather_tile_kernel<T><<<(unsigned)grid, GA_THREADS, smem, st>>>(src, stride_a, nrows, rowlen, K, offs, out);
+        return after_launch();
+    }
     int chunk = 128;
     if (K > 256) chunk = 16;   // 3-D: 792 values per voxel
     const int64_t work = nrows * ((rowlen + chunk - 1) / chunk);
