@@ -35,9 +35,14 @@ def line_profile_v2(image_padded, patch_size, theta_range, phi_range):
 
 def line_profile_memory_efficient_v2(image_padded, patch_size, theta_range, phi_range):
     """(Xp,Yp,Zp) -> (X,Y,Z,T): (centre-min)/max(max-min,1e-8) per direction, bio/neighbor.pyx:186-263."""
+    import torch
     from hipr_b200 import ops
-    return _run(lambda v, p, t, f: ops.lne3d_dirs(v, p, t, f, padded=True), image_padded, patch_size, theta_range,
-                phi_range)
+    if isinstance(image_padded, torch.Tensor):
+        return _run(lambda v, p, t, f: ops.lne3d_dirs(v, p, t, f, padded=True), image_padded, patch_size, theta_range,
+                    phi_range)
+    # host arrays: bands of x-planes under the device -> host copy (hipr_lne3d_dirs_host); ordinary numpy result
+    params = [_tables._int_arg(p, "parameter") for p in (patch_size, theta_range, phi_range)]
+    return ops.lne3d_dirs_host(_as_double_2d(image_padded, 3), *params)
 
 
 def line_profile_memory_efficient_v3(image_padded, patch_size, theta_range, phi_range):

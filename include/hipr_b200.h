@@ -222,6 +222,13 @@ int hipr_line_profile_3d(const void *volume_padded_dev, int Xp, int Yp, int Zp, 
 int hipr_lne3d_dirs(const void *volume_dev, int Xs, int Ys, int Zs, int padded, int dtype,
                     int patch_size, int n_dirs, const int32_t *table_host,
                     const uint64_t *maxkey_dev, void *out_dev, void *stream);
+/* line_profile_memory_efficient_v2 from and to HOST arrays (what `from neighbor import
+ * line_profile_memory_efficient_v2`, bio/..._analysis.py:39, :456, :812, binds for numpy callers):
+ * padded float64 volume (Xp, Yp, Zp) in, (X, Y, Z, n_dirs) float64 out (576 B per voxel at 72
+ * directions), computed in bands of x-planes under the device -> host copy of the previous bands
+ * (page-locked out_host directly, pageable through the staging ring).  Blocking. */
+int hipr_lne3d_dirs_host(const double *volume_padded_host, int Xp, int Yp, int Zp, int patch_size,
+                         int n_dirs, const int32_t *table_host, double *out_host);
 int hipr_lne3d(const void *volume_dev, int Xs, int Ys, int Zs, int padded, int dtype,
                int patch_size, int n_dirs, const int32_t *table_host, int flavour,
                const uint64_t *maxkey_dev, void *out_dev, void *stream);

@@ -49,6 +49,21 @@ def test_memory_efficient_v2_vs_compiled_reference(torch_cuda, ref3d):
     np.testing.assert_allclose(got, ref3d.line_profile_memory_efficient_v2(a, 11, 9, 9), rtol=1e-12, atol=1e-15)
 
 
+def test_memory_efficient_v2_host_bands(torch_cuda):
+    """hipr_lne3d_dirs_host: several bands of x-planes, pageable / page-locked / caller's output, all bit-identical to
+    the device operator on the whole volume (which the tests above hold against the oracle and the compiled reference)."""
+    import hipr_b200
+    a = smooth_image((50, 70, 60), 9).astype(np.float64)          # (40, 60, 50, 72) float64 = 69 MB: 3 bands
+    want = hipr_b200.lne3d_dirs(_cuda(torch_cuda, a), 11, 9, 9, padded=True).cpu().numpy()
+    got = hipr_b200.lne3d_dirs_host(a, 11, 9, 9)
+    assert got.shape == (40, 60, 50, 72) and np.array_equal(got, want)
+    assert np.array_equal(hipr_b200.lne3d_dirs_host(a, 11, 9, 9, pinned=True), want)
+    out = np.full(want.shape, -1.0)
+    assert hipr_b200.lne3d_dirs_host(a, 11, 9, 9, out=out) is out and np.array_equal(out, want)
+    with pytest.raises(TypeError):
+        hipr_b200.lne3d_dirs_host(a.astype(np.float32), 11, 9, 9)
+
+
 def test_memory_efficient_v2_flat_lines_clamped(torch_cuda, oracle):
     import neighbor
     a = np.full((15, 15, 15), 0.5)
