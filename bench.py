@@ -296,6 +296,12 @@ def measure_next_rows(cube, labels, with_cpu):
     out["channel_sum_flat_field"] = {"ms": t, "gb_s": npix * 768 / t / 1e6, "bytes_per_px": 768}
     t = gpu_ms(lambda: ops.denoise_nl_means(s64, h=0.02), n=5)
     out["denoise_nl_means"] = {"ms": t, "mpix_s": npix / t / 1e3}
+    # the z-stack caller's denoise (bio-ana:454, h = 0.03) on a 128 x 132 x 54 volume: 12,167 shifts x 216-voxel windows
+    vol3 = (0.5 + 0.05 * torch.rand((128, 132, 54), device=cube.device, dtype=torch.float64))
+    t = gpu_ms(lambda: ops.denoise_nl_means(vol3, h=0.03), n=2)
+    out["denoise_nl_means_3d"] = {"ms": t, "shape": [128, 132, 54], "mvox_s": vol3.numel() / t / 1e3,
+                                  "g_voxel_shifts_s": vol3.numel() * 12167 / t / 1e6}
+    del vol3
     t = gpu_ms(lambda: ops.neighbor2d_score(cube, "F1", denoise_h=0.02), n=5)
     out["chain_sum_denoise_score"] = {"ms": t, "mpix_s": npix / t / 1e3}
     host = ops.pinned_empty(tuple(cube.shape), np.float32)

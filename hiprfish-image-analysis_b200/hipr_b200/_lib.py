@@ -25,6 +25,8 @@ _SIGNATURES = {
     "hipr_range_decode": (_i, [_vp, _vp, _vp]),
     "hipr_range_encode": (_i, [_vp, _vp, _vp]),
     "hipr_denoise_nl_means_2d": (_i, [_vp, _i, _i, _i, _i, _i, C.c_double, _vp, _vp]),
+    "hipr_denoise_nl_means_3d": (_i, [_vp, _i, _i, _i, _i, _i, _i, C.c_double, _vp, _vp, _i64, _vp]),
+    "hipr_denoise_nl_means_3d_workspace": (_i64, [_i, _i, _i, _i]),
     "hipr_line_profile_2d": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "hipr_lne2d": (_i, [_vp, _i, _i, _i64, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp]),
     "hipr_lne2d_q": (_i, [_vp, _i, _i, _i64, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp]),

@@ -175,11 +175,25 @@ def neighbor2d_score_from_stacks(stacks, shifts=None, calibration=None, flavour=
 
 def denoise_nl_means(image, patch_size=7, patch_distance=11, h=0.1):
     """skimage.restoration.denoise_nl_means(image, h=h) for a 2-D image (fast mode, sigma 0), as
-    syn/...measurement.py:108 calls it on the normalised sum image.  (H, W) float32 / float64 CUDA tensor ->
-    same dtype.  csrc/nlm2d.cu; patch_size 7, patch_distance <= 15."""
+    syn/...measurement.py:108 calls it on the normalised sum image, or for a 3-D volume as bio/...analysis.py:454
+    calls it on a z-stack.  (H, W) / (X, Y, Z) float32 / float64 CUDA tensor -> same dtype.  csrc/nlm2d.cu,
+    csrc/nlm3d.cu; patch_size 7, patch_distance <= 15."""
     image = _dev(image, "image")
+    if image.dim() == 3:
+        # a z-stack volume (bio/...analysis.py:454, h = 0.03): csrc/nlm3d.cu
+        X, Y, Z = image.shape
+        need = int(lib().hipr_denoise_nl_means_3d_workspace(X, Y, Z, int(patch_distance)))
+        if need < 0:
+            raise ValueError("patch_distance must be in [0, 15]")
+        work = torch.empty(need, dtype=torch.uint8, device=image.device)
+        out = torch.empty_like(image)
+        with torch.cuda.device(image.device):
+            check(lib().hipr_denoise_nl_means_3d(C.c_void_p(image.data_ptr()), X, Y, Z, _DT[image.dtype], int(patch_size),
+                                                 int(patch_distance), float(h), C.c_void_p(out.data_ptr()),
+                                                 C.c_void_p(work.data_ptr()), need, _stream()), "denoise_nl_means_3d")
+        return out
     if image.dim() != 2:
-        raise ValueError("image must be 2-D, got %d-D" % image.dim())
+        raise ValueError("image must be 2-D or 3-D, got %d-D" % image.dim())
     Hh, Ww = image.shape
     out = torch.empty_like(image)
     with torch.cuda.device(image.device):

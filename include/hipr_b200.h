@@ -132,6 +132,16 @@ int hipr_range_encode(const double *maxmin_dev, uint64_t *range_dev, void *strea
 int hipr_denoise_nl_means_2d(const void *image_dev, int H, int W, int dtype, int patch_size,
                              int patch_distance, double h, void *out_dev, void *stream);
 
+/* The same for a z-stack: skimage.restoration.denoise_nl_means(volume, h = 0.03) on the (X, Y, Z) normalised sum
+ * volume, bio/..._analysis.py:454 (fast mode, patch_size 7, patch_distance 11, sigma 0; a 3-D array read as a
+ * volume, scikit-image >= 0.15 -- parity unpinned like the 2-D form).  volume_dev, out_dev (X, Y, Z) of dtype;
+ * X, Y, Z > offset + patch_distance + 1.  workspace_dev: hipr_denoise_nl_means_3d_workspace(X, Y, Z,
+ * patch_distance) bytes of device memory (the reflect-padded float64 copy); HIPR_E_RANGE if smaller. */
+int hipr_denoise_nl_means_3d(const void *volume_dev, int X, int Y, int Z, int dtype, int patch_size,
+                             int patch_distance, double h, void *out_dev, void *workspace_dev,
+                             int64_t workspace_bytes, void *stream);
+int64_t hipr_denoise_nl_means_3d_workspace(int X, int Y, int Z, int patch_distance);
+
 /* ---- 2-D literal stencil ------------------------------------------------------------------
  * Replaces line_profile_2d_v2(image_padded, patch_size, phi_range), eco/neighbor2d.pyx:8-64:
  *   out[i, j, t, li] = image_padded[i + table[t, li, 0], j + table[t, li, 1]]

@@ -359,6 +359,104 @@ def denoise_nl_means_2d_direct(image, patch_size=7, patch_distance=11, h=0.1):
     return acc_v / acc_w
 
 
+def denoise_nl_means_3d(image, patch_size=7, patch_distance=11, h=0.1, sigma=0.0):
+    """skimage.restoration.denoise_nl_means(volume, h=h) for a 3-D grayscale volume (multichannel=False, fast mode),
+    as the z-stack caller uses it: bio/hiprfish_imaging_biofilm_analysis.py:454 (h = 0.03).
+
+    PARITY UNPINNED, twice over: scikit-image is neither vendored nor pinned by the reference and is not installed
+    here; and its era matters -- scikit-image <= 0.14 treats a 3-D array with multichannel=None as a 2-D image with
+    Z channels (deprecation warning), 0.15+ as a volume.  This restates the published algorithm of
+    skimage/restoration/_nl_means_denoising.pyx::_fast_nl_means_denoising_3d (the volume reading), loop for loop:
+      * reflect padding by offset + d + 1;
+      * for every shift (t_pln, t_row in [-d, d], t_col in [0, d]): 3-D integral image of (padded - shifted)^2
+        - 2 sigma^2, patch distance by inclusion-exclusion over its eight corners at +-offset (a 2*offset cube),
+        clipped at 0 and divided by h^2 * patch_size^3;
+      * weight = alpha * exp(-distance) unless distance > 5, alpha = 0.5 on the t_col = 0 plane except the zero
+        shift; accumulated symmetrically into both voxels of the pair;
+      * result / weights, cropped.
+    Vectorised over voxels, one shift at a time ((2d + 1)^2 (d + 1) shifts: minutes for d = 11 on a 20^3 volume).
+    Test infrastructure only."""
+    image = np.asarray(image, dtype=np.float64)
+    if image.ndim != 3:
+        raise ValueError("3-D grayscale volumes only")
+    s = int(patch_size)
+    if s % 2 == 0:
+        s += 1
+    d = int(patch_distance)
+    o = s // 2
+    pad_size = o + d + 1
+    padded = np.pad(image, pad_size, mode="reflect")
+    n_pln, n_row, n_col = padded.shape
+    result = np.zeros_like(padded)
+    weights = np.zeros_like(padded)
+    h2s3 = h * h * s * s * s
+    var = 2.0 * sigma * sigma
+    for t_pln in range(-d, d + 1):
+        p0, p1 = max(o, o - t_pln), min(n_pln - o, n_pln - o - t_pln)
+        pa, pb = max(1, -t_pln), min(n_pln, n_pln - t_pln)
+        for t_row in range(-d, d + 1):
+            r0, r1 = max(o, o - t_row), min(n_row - o, n_row - o - t_row)
+            ra, rb = max(1, -t_row), min(n_row, n_row - t_row)
+            for t_col in range(0, d + 1):
+                alpha = 0.5 if (t_col == 0 and (t_pln != 0 or t_row != 0)) else 1.0
+                c0, c1 = o, n_col - o - t_col
+                ca, cb = 1, n_col - t_col
+                integral = np.zeros_like(padded)
+                diff = (padded[pa:pb, ra:rb, ca:cb] - padded[pa + t_pln:pb + t_pln, ra + t_row:rb + t_row, ca + t_col:cb + t_col]) ** 2 - var
+                integral[pa:pb, ra:rb, ca:cb] = np.cumsum(np.cumsum(np.cumsum(diff, axis=0), axis=1), axis=2)
+
+                def I(dp, dr, dc):
+                    return integral[p0 + dp:p1 + dp, r0 + dr:r1 + dr, c0 + dc:c1 + dc]
+                dist = (I(o, o, o) - I(-o, o, o) - I(o, -o, o) - I(o, o, -o)
+                        + I(-o, -o, o) + I(-o, o, -o) + I(o, -o, -o) - I(-o, -o, -o))
+                dist = np.maximum(dist, 0.0) / h2s3
+                w = np.where(dist > NLM_DISTANCE_CUTOFF, 0.0, alpha * np.exp(-dist))
+                A = (slice(p0, p1), slice(r0, r1), slice(c0, c1))
+                B = (slice(p0 + t_pln, p1 + t_pln), slice(r0 + t_row, r1 + t_row), slice(c0 + t_col, c1 + t_col))
+                weights[A] += w
+                weights[B] += w
+                result[A] += w * padded[B]
+                result[B] += w * padded[A]
+    c = slice(pad_size, -pad_size)
+    return result[c, c, c] / weights[c, c, c]
+
+
+def denoise_nl_means_3d_direct(image, patch_size=7, patch_distance=11, h=0.1):
+    """The same estimator voxel by voxel (no integral images, no symmetric accumulation): for every voxel p and every
+    shift t in [-d, d]^3, weight = exp(-max(sum over the 2*offset cube p - offset + 1 .. p + offset of
+    (v[u] - v[u + t])^2, 0) / (h^2 s^3)) if that distance is <= 5, the zero shift counted twice.  This is the form the
+    CUDA kernel evaluates; used to check the restatement above against an independent formulation."""
+    image = np.asarray(image, dtype=np.float64)
+    s = int(patch_size) | 1
+    d = int(patch_distance)
+    o = s // 2
+    pad = o + d + 1
+    v = np.pad(image, pad, mode="reflect")
+    X, Y, Z = image.shape
+    h2s3 = h * h * s * s * s
+    acc_w = np.zeros((X, Y, Z))
+    acc_v = np.zeros((X, Y, Z))
+    lo, n = -o + 1, 2 * o
+    a = v[pad + lo: pad + X + o, pad + lo: pad + Y + o, pad + lo: pad + Z + o]
+    for tx in range(-d, d + 1):
+        for ty in range(-d, d + 1):
+            for tz in range(-d, d + 1):
+                b = v[pad + lo + tx: pad + X + o + tx, pad + lo + ty: pad + Y + o + ty, pad + lo + tz: pad + Z + o + tz]
+                D = (a - b) ** 2
+                box = np.zeros((X, Y, Z))
+                for i in range(n):
+                    for j in range(n):
+                        for k in range(n):
+                            box += D[i:i + X, j:j + Y, k:k + Z]
+                dist = np.maximum(box, 0.0) / h2s3
+                w = np.where(dist > NLM_DISTANCE_CUTOFF, 0.0, np.exp(-dist))
+                if tx == 0 and ty == 0 and tz == 0:
+                    w = 2.0 * w
+                acc_w += w
+                acc_v += w * v[pad + tx: pad + tx + X, pad + ty: pad + ty + Y, pad + tz: pad + tz + Z]
+    return acc_v / acc_w
+
+
 def _mean_quartiles(rnc, axis):
     m = np.average(rnc, axis=axis)
     with np.errstate(invalid="ignore"):

@@ -75,3 +75,45 @@ def test_nlm_argument_errors(torch_cuda):
         hipr_b200.denoise_nl_means(img.cpu())
     flat = torch_cuda.full((32, 32), 0.25, device="cuda", dtype=torch_cuda.float64)
     assert torch_cuda.allclose(hipr_b200.denoise_nl_means(flat, h=0.02), flat, rtol=1e-13, atol=0)
+
+
+def _volume(shape, seed, noise=0.03):
+    rng = np.random.default_rng(seed)
+    x, y, z = np.meshgrid(*[np.arange(n) for n in shape], indexing="ij")
+    v = (np.sin(x / 4.0) ** 2 + np.cos(y / 5.0) ** 2 + np.sin(z / 6.0 + 1.0) ** 2) / 3 + noise * rng.random(shape)
+    return v / v.max()
+
+
+@pytest.mark.parametrize("shape,h,d", [((9, 12, 30), 0.05, 2), ((17, 13, 29), 0.03, 3), ((10, 24, 56), 0.1, 4),
+                                        ((8, 11, 27), 0.02, 3)])
+def test_nlm3d_matches_oracle(torch_cuda, oracle, shape, h, d):
+    """csrc/nlm3d.cu against the loop-for-loop restatement of skimage's _fast_nl_means_denoising_3d (small search
+    distances: the numpy oracle needs (2d + 1)^2 (d + 1) passes); several tiles per axis, ragged edges."""
+    import hipr_b200
+    vol = _volume(shape, shape[0] + d)
+    want = oracle.denoise_nl_means_3d(vol, patch_distance=d, h=h)
+    got = hipr_b200.denoise_nl_means(torch_cuda.from_numpy(vol).cuda(), patch_distance=d, h=h)
+    assert got.dtype == torch_cuda.float64 and tuple(got.shape) == shape
+    np.testing.assert_allclose(got.cpu().numpy(), want, rtol=RTOL_NLM, atol=0)
+    got32 = hipr_b200.denoise_nl_means(torch_cuda.from_numpy(vol.astype(np.float32)).cuda(), patch_distance=d, h=h)
+    want32 = oracle.denoise_nl_means_3d(vol.astype(np.float32), patch_distance=d, h=h)
+    np.testing.assert_allclose(got32.cpu().numpy(), want32, rtol=2e-7 + RTOL_NLM, atol=0)
+
+
+def test_nlm3d_caller_parameters_golden(torch_cuda):
+    """patch 7, distance 11, h = 0.03 (bio/..._analysis.py:454) against the frozen output of the oracle
+    (tests/golden/make_golden_nlm3d.py: minutes of numpy)."""
+    import os
+    import hipr_b200
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "nlm3d_vectors.npz"))
+    got = hipr_b200.denoise_nl_means(torch_cuda.from_numpy(g["nlm3d_in"]).cuda(), h=0.03)
+    np.testing.assert_allclose(got.cpu().numpy(), g["nlm3d_out_h003"], rtol=RTOL_NLM, atol=0)
+
+
+def test_nlm3d_rejects_small_volumes_and_bad_parameters(torch_cuda):
+    import hipr_b200
+    v = torch_cuda.rand((12, 40, 40), dtype=torch_cuda.float64, device="cuda")
+    with pytest.raises((ValueError, hipr_b200.HiprError)):
+        hipr_b200.denoise_nl_means(v, h=0.03)                      # 12 <= offset + d + 1 = 15: np.pad would reflect twice
+    with pytest.raises((ValueError, hipr_b200.HiprError)):
+        hipr_b200.denoise_nl_means(v, patch_size=5, patch_distance=2, h=0.03)

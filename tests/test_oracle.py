@@ -200,3 +200,24 @@ def test_oracle_next_rows_match_frozen_vectors(oracle):
     assert np.array_equal(lab, g["geo_labels"]) and np.array_equal(area, g["geo_area"])
     np.testing.assert_allclose(geom, g["geo_geometry"], rtol=1e-13, atol=1e-13)
     assert np.array_equal(oracle.paint_labels(g["geo_seg"], g["paint_values"]), g["paint_out"])
+
+
+@pytest.mark.parametrize("h,d", [(0.05, 2), (0.03, 3)])
+def test_nlm3d_restatement_equals_direct_formulation(oracle, h, d):
+    """The loop-for-loop restatement of skimage's _fast_nl_means_denoising_3d (integral images, symmetric
+    accumulation) against the voxel-by-voxel form the CUDA kernel evaluates."""
+    rng = np.random.default_rng(7)
+    x, y, z = np.meshgrid(np.arange(9), np.arange(10), np.arange(11), indexing="ij")
+    vol = 0.5 + 0.3 * np.sin(x / 2.0 + y / 3.0) * np.cos(z / 2.5) + 0.02 * rng.standard_normal((9, 10, 11))
+    a = oracle.denoise_nl_means_3d(vol, patch_distance=d, h=h)
+    b = oracle.denoise_nl_means_3d_direct(vol, patch_distance=d, h=h)
+    np.testing.assert_allclose(a, b, rtol=1e-12)
+    flat = np.full((9, 10, 11), 0.25)
+    np.testing.assert_allclose(oracle.denoise_nl_means_3d(flat, patch_distance=d, h=h), flat, rtol=1e-13)
+
+
+def test_nlm3d_golden_vectors_present():
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "nlm3d_vectors.npz"))
+    assert g["nlm3d_in"].shape == g["nlm3d_out_h003"].shape == (17, 18, 40)
+    assert np.all(np.isfinite(g["nlm3d_out_h003"])) and np.abs(g["nlm3d_out_h003"] - g["nlm3d_in"]).max() < 0.2
