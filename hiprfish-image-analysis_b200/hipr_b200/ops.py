@@ -533,12 +533,15 @@ def lne3d_fixed(volume, flavour="ME2", patch_size=11, theta_range=9, phi_range=9
     return out
 
 
-def neighbor3d_score(cube, flavour="ME2", patch_size=11, theta_range=9, phi_range=9, dtype=None):
+def neighbor3d_score(cube, flavour="ME2", patch_size=11, theta_range=9, phi_range=9, dtype=None, denoise_h=None,
+                     denoise_distance=11):
     """cube (X, Y, Z, C) float32 -> score volume (X, Y, Z): channel sum -> /max -> edge pad ->
     3-D line profiles -> epilogue (bio/...analysis.py:807-817 for 'ME2').  dtype=None: float64 sums +
     fixed-point stencil (float32 score); torch.float32 / float64: floating-point stencil of that type.
     A batch (N, X, Y, Z, C) of independent z-stacks alternates between two streams, so that the channel sum of
-    stack i+1 (HBM-bound) runs beside the stencil of stack i (ALU-bound); returns (N, X, Y, Z)."""
+    stack i+1 (HBM-bound) runs beside the stencil of stack i (ALU-bound); returns (N, X, Y, Z).
+    denoise_h: with the NL-means denoise of bio/...analysis.py:454 (h = 0.03 there) between the normalisation and the
+    stencil (csrc/nlm3d.cu, float64 stencil after it)."""
     cube = _dev(cube, "cube", (torch.float32,))
     if cube.dim() == 5:
         cur = torch.cuda.current_stream(cube.device)
@@ -548,7 +551,7 @@ def neighbor3d_score(cube, flavour="ME2", patch_size=11, theta_range=9, phi_rang
         res = []
         for i, c in enumerate(cube):
             with torch.cuda.stream(side[i % len(side)]):
-                res.append(neighbor3d_score(c, flavour, patch_size, theta_range, phi_range, dtype))
+                res.append(neighbor3d_score(c, flavour, patch_size, theta_range, phi_range, dtype, denoise_h, denoise_distance))
         for st in side:
             cur.wait_stream(st)
         for r in res:
@@ -556,6 +559,12 @@ def neighbor3d_score(cube, flavour="ME2", patch_size=11, theta_range=9, phi_rang
         return torch.stack(res)
     if cube.dim() != 4:
         raise ValueError("cube must be (X, Y, Z, C) or (N, X, Y, Z, C)")
+    if denoise_h is not None:
+        # bio/...analysis.py:452-462 in full: sum -> /max -> denoise_nl_means(h) -> edge pad -> me_v2 -> epilogue; the
+        # denoised volume is too smooth for the fixed-point grid (as in 2-D): float64 stencil
+        s = channel_sum(cube, None, normalize=True, dtype=torch.float64)
+        den = denoise_nl_means(s, patch_distance=denoise_distance, h=denoise_h)
+        return lne3d(den, flavour, patch_size, theta_range, phi_range, padded=False)
     s, mk = channel_sum(cube, None, normalize=False, dtype=dtype or torch.float64, return_max=True)
     if dtype is None:
         res = lne3d_fixed(s, flavour, patch_size, theta_range, phi_range, padded=False, maxkey=mk)

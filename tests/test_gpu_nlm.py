@@ -117,3 +117,18 @@ def test_nlm3d_rejects_small_volumes_and_bad_parameters(torch_cuda):
         hipr_b200.denoise_nl_means(v, h=0.03)                      # 12 <= offset + d + 1 = 15: np.pad would reflect twice
     with pytest.raises((ValueError, hipr_b200.HiprError)):
         hipr_b200.denoise_nl_means(v, patch_size=5, patch_distance=2, h=0.03)
+
+
+def test_chain3d_sum_denoise_score(torch_cuda, oracle):
+    """The z-stack chain of bio/..._analysis.py:452-462: channel sum -> /max -> NL-means -> edge pad ->
+    line_profile_memory_efficient_v2 -> mean * (1 - qcv), device-resident, against the oracle chain (search distance 3
+    so that the numpy oracle finishes in seconds; the caller's distance 11 is covered by the golden-vector test)."""
+    import hipr_b200
+    from hipr_b200 import synth
+    cube = synth.make_volume_cube(10, 12, 30, 95, seed=4)
+    s = cube.numpy().astype(np.float64).sum(axis=3)
+    s = s / s.max()
+    den = oracle.denoise_nl_means_3d(s, patch_distance=3, h=0.03)
+    want = oracle.lne3d(den, "ME2")
+    got = hipr_b200.neighbor3d_score(cube.cuda(), "ME2", denoise_h=0.03, denoise_distance=3)
+    np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-6, atol=1e-9)
