@@ -13,12 +13,14 @@
 // 140 times a 2-D image of the same voxel count, which is why the separable running sums below matter.
 //
 // A pad kernel first writes the reflect-padded volume (pad offset + d + 1 = 15, as skimage; dimensions rounded up to
-// whole tiles) so that every shifted read is one linear offset.  A CTA (8 warps) owns an 8 x 11 x 27 output tile: its
+// whole tiles) so that every shifted read is one linear offset.  A CTA (16 warps) owns an 8 x 11 x 27 output tile: its
 // unshifted 13 x 16 x 32 window region sits in shared memory (z along the 32 lanes: 27 + 5 = one warp width).  Per shift:
-//   phase 1  warp w, lane k: for region rows j = w and w + 8, the 13 squared differences along x (shifted samples
-//            straight from global memory / L1: coalesced rows of 32 doubles) and their eight sliding 6-sums -> Sx[x][j][k];
-//   phase 2  warp = x, lane k: sixteen Sx[x][.][k], eleven sliding 6-sums along y in registers, then the 6-sum along z
-//            across lanes (shuffles), exp, accumulate weight and weighted value for eleven voxels per thread.
+//   phase 1  warp j, lane k: for region row j, the 13 squared differences along x (shifted samples straight from
+//            global memory / L1: coalesced rows of 32 doubles) and their eight sliding 6-sums -> Sx[x][j][k];
+//   phase 2  warp = (plane x, half of the rows), lane k: eleven Sx[x][.][k], six sliding 6-sums along y in registers,
+//            then the 6-sum along z across lanes (shuffles), exp, accumulate weight and weighted value for six voxels
+//            per thread (first version: 8 warps, two rows / eleven voxels per thread, 154 registers: 102 ms per
+//            128 x 132 x 54 volume, latency-bound at two warps per scheduler).
 // Sx is double-buffered (phase 1 of shift i + 1 precedes phase 2 of shift i): one __syncthreads per shift.
 // Everything is float64, for the reason given in nlm2d.cu (the hard cutoff).
 #include "hipr_common.cuh"
@@ -31,7 +33,9 @@ constexpr int N3_OFF = 3, N3_N = 2 * N3_OFF;                 // patch 7: window 
 constexpr int N3_RX = N3_TX + N3_N - 1;                      // 13 region planes
 constexpr int N3_RY = N3_TY + N3_N - 1;                      // 16 region rows
 constexpr int N3_RZ = N3_TZ + N3_N - 1;                      // 32 region columns = lanes
-static_assert(N3_RZ == 32 && N3_RY == 16 && N3_TX == 8, "the thread mapping below assumes these");
+constexpr int N3_THREADS = 512;                              // 16 warps: one region row each in phase 1, (plane, half of the rows) in phase 2
+constexpr int N3_NQ = 6;                                     // voxels per thread in phase 2 (rows 0..5 / 6..10)
+static_assert(N3_RZ == 32 && N3_RY == 16 && N3_TX == 8 && N3_THREADS == 32 * N3_RY && 2 * N3_NQ >= N3_TY, "the thread mapping below assumes these");
 
 // reflect-padded copy (np.pad(mode='reflect') by `pad`), dimensions (Xp, Yp, Zp) >= (X, Y, Z) + 2 pad; cells beyond
 // the padded volume (tile round-up) are zero and never reach a written voxel
@@ -51,7 +55,7 @@ __global__ void nlm3d_pad_kernel(const T *__restrict__ vol, int X, int Y, int Z,
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(N3_THREADS, 1)
 nlm3d_kernel(const double *__restrict__ vp, int Yp, int Zp, int pad, int X, int Y, int Z, int d, double inv_h2s3,
              T *__restrict__ out) {
     extern __shared__ __align__(16) double n3_smem[];
@@ -64,43 +68,40 @@ nlm3d_kernel(const double *__restrict__ vp, int Yp, int Zp, int pad, int X, int 
     const int64_t plane = (int64_t)Yp * Zp;
     // region origin in the padded volume: tile origin - offset + 1
     const double *rbase = vp + ((int64_t)(x0 + pad - N3_OFF + 1) * Yp + (y0 + pad - N3_OFF + 1)) * Zp + (z0 + pad - N3_OFF + 1);
-    for (int i = tid; i < N3_RX * N3_RY * N3_RZ; i += 256) {
+    for (int i = tid; i < N3_RX * N3_RY * N3_RZ; i += N3_THREADS) {
         const int k = i & 31, j = (i >> 5) & 15, ii = i >> 9;
         A[i] = rbase[ii * plane + (int64_t)j * Zp + k];
     }
     __syncthreads();
-    // phase 1: rows j = warp and warp + 8 of the region, column k = lane
+    // phase 1: row j = warp of the region, column k = lane
     const double *a1 = A + warp * N3_RZ + lane;
     const double *b1 = rbase + (int64_t)warp * Zp + lane;
     auto phase1 = [&](int64_t soff, int which) {
         double *dst = Sx + which * SXN + warp * N3_RZ + lane;
+        const double *b = b1 + soff;
+        double D[N3_RX];
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            const double *a = a1 + half * 8 * N3_RZ;
-            const double *b = b1 + soff + (int64_t)half * 8 * Zp;
-            double D[N3_RX];
+        for (int i = 0; i < N3_RX; ++i) {
+            const double df = a1[i * N3_RY * N3_RZ] - __ldg(b + i * plane);
+            D[i] = df * df;
+        }
+        double s = D[0];
 #pragma unroll
-            for (int i = 0; i < N3_RX; ++i) {
-                const double df = a[i * N3_RY * N3_RZ] - __ldg(b + i * plane);
-                D[i] = df * df;
-            }
-            double s = D[0];
+        for (int i = 1; i < N3_N; ++i) s += D[i];
+        dst[0] = s;
 #pragma unroll
-            for (int i = 1; i < N3_N; ++i) s += D[i];
-            dst[half * 8 * N3_RZ] = s;
-#pragma unroll
-            for (int x = 1; x < N3_TX; ++x) {
-                s += D[x + N3_N - 1] - D[x - 1];               // sliding window along x
-                dst[x * N3_RY * N3_RZ + half * 8 * N3_RZ] = s;
-            }
+        for (int x = 1; x < N3_TX; ++x) {
+            s += D[x + N3_N - 1] - D[x - 1];               // sliding window along x
+            dst[x * N3_RY * N3_RZ] = s;
         }
     };
-    // phase 2: plane x = warp of the tile, column lane; voxels (x, y = 0..10, z = lane) for lane < 27
-    double acc_w[N3_TY], acc_v[N3_TY];
+    // phase 2: plane px = warp & 7 of the tile, rows yb .. yb + 5 (yb = 0 or 6; row 11 does not exist), column lane
+    const int px = warp & 7, yb = (warp >> 3) * N3_NQ;
+    double acc_w[N3_NQ], acc_v[N3_NQ];
 #pragma unroll
-    for (int q = 0; q < N3_TY; ++q) acc_w[q] = acc_v[q] = 0.0;
-    // centre of voxel (x0 + warp, y0, z0 + lane) in the padded volume
-    const double *vc = vp + ((int64_t)(x0 + warp + pad) * Yp + (y0 + pad)) * Zp + (z0 + pad) + lane;
+    for (int q = 0; q < N3_NQ; ++q) acc_w[q] = acc_v[q] = 0.0;
+    // centre of voxel (x0 + px, y0 + yb, z0 + lane) in the padded volume
+    const double *vc = vp + ((int64_t)(x0 + px + pad) * Yp + (y0 + yb + pad)) * Zp + (z0 + pad) + lane;
     const bool lane_on = lane < N3_TZ;
     const int side = 2 * d + 1;
     const int nshift = side * side * side;
@@ -114,15 +115,15 @@ nlm3d_kernel(const double *__restrict__ vp, int Yp, int Zp, int pad, int X, int 
     for (int s = 0; s < nshift; ++s) {
         if (s + 1 < nshift) phase1(shift_off(s + 1), buf ^ 1);
         const int64_t soff = shift_off(s);
-        const double *hcur = Sx + buf * SXN + warp * N3_RY * N3_RZ + lane;
-        double hs[N3_RY];
+        const double *hcur = Sx + buf * SXN + px * N3_RY * N3_RZ + lane;
+        double hs[N3_NQ + N3_N - 1];
 #pragma unroll
-        for (int j = 0; j < N3_RY; ++j) hs[j] = hcur[j * N3_RZ];
+        for (int j = 0; j < N3_NQ + N3_N - 1; ++j) hs[j] = hcur[min(yb + j, N3_RY - 1) * N3_RZ];   // row 16 only feeds the unused row 11
         double sy = hs[0];
 #pragma unroll
         for (int j = 1; j < N3_N; ++j) sy += hs[j];
 #pragma unroll
-        for (int q = 0; q < N3_TY; ++q) {
+        for (int q = 0; q < N3_NQ; ++q) {
             if (q > 0) sy += hs[q + N3_N - 1] - hs[q - 1];     // sliding window along y
             // 6-sum along z: lanes l .. l + 5 (lanes >= 27 produce unused values)
             double box = sy;
@@ -131,21 +132,22 @@ nlm3d_kernel(const double *__restrict__ vp, int Yp, int Zp, int pad, int X, int 
             const double dist = fabs(box) * inv_h2s3;
             const int hi = __double2hiint(dist);
             const bool inside = (hi < 0x40140000) || (hi == 0x40140000 && __double2loint(dist) == 0);   // dist <= 5.0
+            const bool on = lane_on && yb + q < N3_TY;
             double w = exp_small_neg(-dist);
-            w = (inside && lane_on) ? w : 0.0;
-            const double v = lane_on ? __ldg(vc + soff + (int64_t)q * Zp) : 0.0;
+            w = (inside && on) ? w : 0.0;
+            const double v = on ? __ldg(vc + soff + (int64_t)q * Zp) : 0.0;
             acc_w[q] += w;
             acc_v[q] = fma(w, v, acc_v[q]);
         }
         buf ^= 1;
         __syncthreads();
     }
-    const int x = x0 + warp, z = z0 + lane;
+    const int x = x0 + px, z = z0 + lane;
     if (lane_on && x < X && z < Z) {
 #pragma unroll
-        for (int q = 0; q < N3_TY; ++q) {
-            const int y = y0 + q;
-            if (y >= Y) break;
+        for (int q = 0; q < N3_NQ; ++q) {
+            const int y = y0 + yb + q;
+            if (yb + q >= N3_TY || y >= Y) break;
             // the zero shift counts twice
             const double w = acc_w[q] + 1.0, v = acc_v[q] + vc[(int64_t)q * Zp];
             out[((int64_t)x * Y + y) * Z + z] = (T)(v / w);
@@ -192,9 +194,9 @@ extern "C" int hipr_denoise_nl_means_3d(const void *volume_dev, int X, int Y, in
     const double inv = 1.0 / (h * h * 343.0);
     const unsigned grid = (unsigned)((int64_t)nxb * nyb * nzb);
     if (dtype == HIPR_F32)
-        nlm3d_kernel<float><<<grid, 256, smem, st>>>(vp, Yp, Zp, pad, X, Y, Z, d, inv, (float *)out_dev);
+        nlm3d_kernel<float><<<grid, N3_THREADS, smem, st>>>(vp, Yp, Zp, pad, X, Y, Z, d, inv, (float *)out_dev);
     else
-        nlm3d_kernel<double><<<grid, 256, smem, st>>>(vp, Yp, Zp, pad, X, Y, Z, d, inv, (double *)out_dev);
+        nlm3d_kernel<double><<<grid, N3_THREADS, smem, st>>>(vp, Yp, Zp, pad, X, Y, Z, d, inv, (double *)out_dev);
     return after_launch();
 }
 
