@@ -1,10 +1,10 @@
 // K6-3D: non-local-means denoise of the (X, Y, Z) channel-sum volume -- the step between the channel sum and the
 // 72-direction stencil in the z-stack caller: skimage.restoration.denoise_nl_means(volume, h = 0.03),
 // bio/..._analysis.py:454, fast mode, patch_size 7, patch_distance 11, sigma 0 (scikit-image >= 0.15 semantics: a
-// 3-D array is a volume; see the oracle's docstring for the <= 0.14 ambiguity).
+// 3-D array is a volume; INTEGRATION.md section 4 for the <= 0.14 ambiguity).
 //
 // scikit-image builds one 3-D integral image of squared differences per patch shift and accumulates each pair of
-// voxels symmetrically.  Voxel by voxel that is (oracle: denoise_nl_means_3d_direct, equal to the loop-for-loop
+// voxels symmetrically.  Voxel by voxel that is (the test side's denoise_nl_means_3d_direct, equal to its loop-for-loop
 // restatement to 1e-15):
 //     out[p] = sum_t w(p, t) v[p + t] / sum_t w(p, t),      t in [-d, d]^3,  twice the weight for t = 0,
 //     w(p, t) = exp(-dist) if dist <= 5 else 0,

@@ -177,3 +177,34 @@ def test_mosaic_peer_buffer_layout_and_argument_checks():
     assert lib.hipr_cell_spectra_host_fetch(0, None, None, None, None) == -1
     assert lib.hipr_register_stacks(None, None, None, None, 0, 1, 1, None, None, None, None, None) == -1
     assert lib.hipr_denoise_nl_means_2d(None, 64, 64, 1, 7, 11, 0.02, None, None) == -1
+
+
+def test_round2_host_entry_points_argument_checks():
+    """Argument validation of the entry points added for the host drop-ins and the 3-D denoise, without any device
+    call: NULL buffers, bad tables, volumes smaller than the reflection pad, workspace arithmetic."""
+    import ctypes as C
+    import numpy as np
+    import hipr_b200
+    from hipr_b200 import tables
+    lib = hipr_b200.lib()
+    tab = np.ascontiguousarray(tables.line_table_2d(11, 9), dtype=np.int32)
+    tp = tab.ctypes.data_as(C.c_void_p)
+    img = np.zeros((20, 20))
+    ip = img.ctypes.data_as(C.c_void_p)
+    assert lib.hipr_line_profile_2d_host(None, 20, 20, 11, 9, tp, ip) == -1
+    assert lib.hipr_line_profile_2d_host(ip, 20, 20, 11, 9, tp, None) == -1
+    assert lib.hipr_line_profile_2d_host(ip, 20, 20, 11, 9, None, ip) != 0            # no table
+    assert lib.hipr_line_profile_2d_host(ip, 8, 20, 11, 9, tp, ip) != 0               # image smaller than the patch
+    assert lib.hipr_lne3d_dirs_host(None, 20, 20, 20, 11, 72, None, ip) == -1
+    assert lib.hipr_lne3d_dirs_host(ip, 8, 20, 20, 11, 72, None, ip) != 0
+    # 3-D denoise: the workspace is the reflect-padded float64 volume, dimensions rounded up to 8 x 11 x 27 tiles
+    pad = 3 + 11 + 1
+    X, Y, Z = 17, 18, 40
+    want = (24 + 2 * pad) * (22 + 2 * pad) * (54 + 2 * pad) * 8
+    assert lib.hipr_denoise_nl_means_3d_workspace(X, Y, Z, 11) == want
+    assert lib.hipr_denoise_nl_means_3d_workspace(X, Y, Z, 16) < 0
+    assert lib.hipr_denoise_nl_means_3d(None, X, Y, Z, 1, 7, 11, 0.03, None, None, 0, None) == -1
+    assert lib.hipr_denoise_nl_means_3d(ip, X, Y, Z, 1, 5, 11, 0.03, ip, ip, want, None) != 0      # patch_size 5: unsupported
+    assert lib.hipr_denoise_nl_means_3d(ip, 15, Y, Z, 1, 7, 11, 0.03, ip, ip, want, None) != 0     # 15 <= pad: np.pad would wrap
+    assert lib.hipr_denoise_nl_means_3d(ip, X, Y, Z, 1, 7, 11, 0.03, ip, ip, want - 8, None) != 0  # workspace too small
+
