@@ -313,6 +313,14 @@ def measure_next_rows(cube, labels, with_cpu):
         ops.neighbor2d_score_host(host, "F1", out=score_host, denoise_h=0.02)
     out["e2e_chain_with_denoise"] = {"ms": 1e3 * (time.perf_counter() - t0) / 3, "mpix_s": npix / ((time.perf_counter() - t0) / 3) / 1e6,
                                      "api": "hipr_neighbor2d_host_denoise (pinned host cube -> score, lines 105-124 in full)"}
+    # the same flow over a batch of FOVs: FOV i + 1 crosses PCIe while FOV i is denoised, scored and read back
+    nb = 4
+    ops.neighbor2d_score_host_batch([host] * 2, "F1", denoise_h=0.02, out=[score_host] * 2)
+    t0 = time.perf_counter()
+    ops.neighbor2d_score_host_batch([host] * nb, "F1", denoise_h=0.02, out=[score_host] * nb)
+    tb = 1e3 * (time.perf_counter() - t0) / nb
+    out["e2e_chain_with_denoise_batch"] = {"ms_per_fov": tb, "mpix_s": npix / tb / 1e3, "fovs": nb,
+                                           "api": "hipr_neighbor2d_host_batch (pinned host cubes -> scores; denoise + stencil of FOV i under the upload of FOV i + 1)"}
     del host
     # a1, the strict drop-in: the literal (H, W, 9, 11) float64 gather of line_profile_2d_v2 (792 B written + 8 read per
     # pixel).  Device-resident against the HBM write roofline, and numpy -> numpy through hipr_line_profile_2d_host

@@ -7,7 +7,20 @@
 #include <cstdlib>
 #include <thread>
 #include <vector>
+#include <cstdio>
 #include "hipr_common.cuh"
+
+// in this file a failing CUDA call also reports where, when HIPR_DEBUG is set (the host pipelines enqueue dozens of
+// calls per entry point; the ABI's return value only carries the code)
+#undef HIPR_CUDA
+#define HIPR_CUDA(expr)                                                                             \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess) {                                                                    \
+            if (getenv("HIPR_DEBUG")) fprintf(stderr, "hipr: %s:%d: %s -> %s\n", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return (int)_e;                                                                         \
+        }                                                                                           \
+    } while (0)
 
 namespace hipr {
 
@@ -35,6 +48,12 @@ struct Workspace {
     void *stage[NBUF] = {};
     size_t stage_bytes = 0;
     cudaEvent_t staged_out[NBUF] = {};   // the H2D copy out of stage[i] has completed
+    // batch entry point (hipr_neighbor2d_host_batch): a third stream for denoise + stencil + score read-back of FOV i
+    // while FOV i + 1 is uploaded and summed, and two sets of per-FOV buffers
+    cudaStream_t post = nullptr;
+    cudaEvent_t summed[2] = {}, post_done[2] = {};
+    void *baux[2][4] = {};
+    size_t baux_bytes[2][4] = {};
     // the cell table of the last hipr_cell_spectra_host call stays in aux[5] for hipr_cell_spectra_host_fetch
     int64_t last_cells = -1, last_max_label = 0;
     int last_C = 0;
@@ -62,6 +81,7 @@ struct DrainOnError {
         if (!armed) return;
         if (w.copy) cudaStreamSynchronize(w.copy);
         if (w.comp) cudaStreamSynchronize(w.comp);
+        if (w.post) cudaStreamSynchronize(w.post);
     }
 };
 
@@ -76,12 +96,23 @@ static int host_copy_threads() {
 static int ws_init(Workspace &w) {
     if (w.ready) return HIPR_OK;
     HIPR_CUDA(cudaStreamCreateWithFlags(&w.copy, cudaStreamNonBlocking));
-    HIPR_CUDA(cudaStreamCreateWithFlags(&w.comp, cudaStreamNonBlocking));
+    // the compute stream (channel sums of the bands as they arrive) has the highest priority: the hardware dispatches a
+    // later kernel's CTAs only when the earlier one has none left to dispatch, unless its stream's priority is higher --
+    // without it a band's channel sum waits behind the whole denoise grid of the previous FOV on the `post` stream, the
+    // band ring fills and the upload stalls (batch entry point: 33.6 ms per FOV instead of the PCIe time)
+    int prio_lo = 0, prio_hi = 0;
+    HIPR_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    HIPR_CUDA(cudaStreamCreateWithPriority(&w.comp, cudaStreamNonBlocking, prio_hi));
     for (int i = 0; i < NBUF; ++i) {
         HIPR_CUDA(cudaEventCreateWithFlags(&w.copied[i], cudaEventDisableTiming));
         HIPR_CUDA(cudaEventCreateWithFlags(&w.freed[i], cudaEventDisableTiming));
     }
     HIPR_CUDA(cudaEventCreateWithFlags(&w.done, cudaEventDisableTiming));
+    HIPR_CUDA(cudaStreamCreateWithFlags(&w.post, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        HIPR_CUDA(cudaEventCreateWithFlags(&w.summed[i], cudaEventDisableTiming));
+        HIPR_CUDA(cudaEventCreateWithFlags(&w.post_done[i], cudaEventDisableTiming));
+    }
     HIPR_CUDA(cudaEventCreate(&w.t0));
     HIPR_CUDA(cudaEventCreate(&w.t1));
     w.ready = true;
@@ -147,6 +178,16 @@ static int ws_aux(Workspace &w, int slot, size_t bytes) {
     w.aux_bytes[slot] = 0;
     HIPR_CUDA(cudaMalloc(&w.aux[slot], bytes));
     w.aux_bytes[slot] = bytes;
+    return HIPR_OK;
+}
+
+static int ws_baux(Workspace &w, int set, int slot, size_t bytes) {
+    if (bytes <= w.baux_bytes[set][slot]) return HIPR_OK;
+    if (w.baux[set][slot]) cudaFree(w.baux[set][slot]);
+    w.baux[set][slot] = nullptr;
+    w.baux_bytes[set][slot] = 0;
+    HIPR_CUDA(cudaMalloc(&w.baux[set][slot], bytes));
+    w.baux_bytes[set][slot] = bytes;
     return HIPR_OK;
 }
 
@@ -224,6 +265,12 @@ extern "C" int hipr_host_release_workspace(void) {
         w.aux[i] = nullptr;
         w.aux_bytes[i] = 0;
     }
+    for (int k = 0; k < 2; ++k)
+        for (int i = 0; i < 4; ++i) {
+            if (w.baux[k][i]) cudaFree(w.baux[k][i]);
+            w.baux[k][i] = nullptr;
+            w.baux_bytes[k][i] = 0;
+        }
     return HIPR_OK;
 }
 
@@ -529,6 +576,104 @@ extern "C" int hipr_neighbor2d_host_denoise(const float *cube_host, int H, int W
     if (!(denoise_h > 0.0)) return HIPR_E_ARG;
     return neighbor2d_host_impl(cube_host, 4, 1.f, H, W, C, patch_size, n_dirs, table_host, flavour, score_host, sum_host,
                                 denoise_h);
+}
+
+// A batch of fields of view from host memory (config 3: hundreds of FOVs per run; the scripts process them one after
+// another, syn/..._measurement.py:161-173 inside the Snakefile's per-sample loop).  FOV i + 1 is uploaded band by band
+// and summed on the copy / compute streams while FOV i's normalisation, NL-means denoise (denoise_h > 0: lines 106-124
+// in full), stencil and score read-back run on a third stream from a second set of buffers: per FOV the call costs the
+// PCIe time of the cube, where one hipr_neighbor2d_host_denoise call per FOV costs that plus ~6 ms of denoise + stencil.
+// Results are bit-identical to the single-FOV entry points.
+extern "C" int hipr_neighbor2d_host_batch(const float *const *cubes_host, int n_fov, int H, int W, int C, int patch_size,
+                                          int n_dirs, const int32_t *table_host, int flavour, double denoise_h,
+                                          float *const *scores_host) {
+    if (!cubes_host || !scores_host || n_fov < 1 || H < 1 || W < 1 || C < 1 || denoise_h < 0.0) return HIPR_E_ARG;
+    for (int i = 0; i < n_fov; ++i)
+        if (!cubes_host[i] || !scores_host[i]) return HIPR_E_ARG;
+    Workspace *wp = ws_current();
+    if (!wp) return HIPR_E_NODEVICE;
+    Workspace &w = *wp;
+    std::lock_guard<std::mutex> lock(w.mu);
+    int e = ws_init(w);
+    if (e) return e;
+    DrainOnError guard(w);
+    const int64_t row_bytes = (int64_t)W * C * 4;
+    const int rows = band_rows(row_bytes, H);
+    if ((e = ws_bands(w, (size_t)rows * row_bytes))) return e;
+    const size_t img_bytes = (size_t)H * W * 4;
+    for (int k = 0; k < 2; ++k) {
+        if ((e = ws_baux(w, k, 0, 4 * img_bytes))) return e;   // float64 sums + float64 denoised image
+        if ((e = ws_baux(w, k, 1, img_bytes))) return e;       // float32 score
+        if ((e = ws_baux(w, k, 2, 64))) return e;              // range keys
+        if ((e = ws_baux(w, k, 3, 2 * img_bytes))) return e;   // float64 score (denoise / general parameters)
+    }
+    const int copy_threads = host_copy_threads();
+    bool any_pageable = false;
+    for (int i = 0; i < n_fov; ++i) any_pageable = any_pageable || is_pageable(cubes_host[i]);
+    if (any_pageable && (e = ws_stage(w, (size_t)rows * row_bytes))) return e;
+    HIPR_CUDA(cudaEventRecord(w.t0, w.copy));
+    HIPR_CUDA(cudaStreamWaitEvent(w.comp, w.t0, 0));
+    HIPR_CUDA(cudaStreamWaitEvent(w.post, w.t0, 0));
+    int b = 0;                                                 // bands since the start of the call (ring slots carry over)
+    for (int i = 0; i < n_fov; ++i) {
+        const int k = i & 1;
+        double *sum_dev = (double *)w.baux[k][0];
+        float *score_dev = (float *)w.baux[k][1];
+        unsigned long long *key = (unsigned long long *)w.baux[k][2];
+        double *score64 = (double *)w.baux[k][3];
+        if (i >= 2) HIPR_CUDA(cudaStreamWaitEvent(w.comp, w.post_done[k], 0));   // FOV i - 2 has left this set
+        HIPR_CUDA(cudaMemsetAsync(key, 0x00, 8, w.comp));
+        HIPR_CUDA(cudaMemsetAsync(key + 1, 0xff, 8, w.comp));
+        const bool pageable = is_pageable(cubes_host[i]);
+        for (int r0 = 0; r0 < H; r0 += rows, ++b) {
+            const int nr = (H - r0 < rows) ? H - r0 : rows;
+            const int slot = b % NBUF;
+            const void *src = (const char *)cubes_host[i] + (int64_t)r0 * row_bytes;
+            if (pageable) {
+                if (b >= NBUF) HIPR_CUDA(cudaEventSynchronize(w.staged_out[slot]));
+                parallel_copy(w.stage[slot], src, (size_t)nr * row_bytes, copy_threads);
+                src = w.stage[slot];
+            }
+            if (b >= NBUF) HIPR_CUDA(cudaStreamWaitEvent(w.copy, w.freed[slot], 0));
+            HIPR_CUDA(cudaMemcpyAsync(w.band[slot], src, (size_t)nr * row_bytes, cudaMemcpyHostToDevice, w.copy));
+            if (any_pageable) HIPR_CUDA(cudaEventRecord(w.staged_out[slot], w.copy));   // (the ring's events exist only then)
+            HIPR_CUDA(cudaEventRecord(w.copied[slot], w.copy));
+            HIPR_CUDA(cudaStreamWaitEvent(w.comp, w.copied[slot], 0));
+            if ((e = chansum_band(w.band[slot], 4, 1.f, (int64_t)nr * W, C, sum_dev + (int64_t)r0 * W, key, w.comp))) return e;
+            HIPR_CUDA(cudaEventRecord(w.freed[slot], w.comp));
+        }
+        HIPR_CUDA(cudaEventRecord(w.summed[k], w.comp));
+        HIPR_CUDA(cudaStreamWaitEvent(w.post, w.summed[k], 0));
+        if (denoise_h > 0.0) {
+            double *den = sum_dev + (size_t)H * W;
+            if ((e = hipr_normalize(sum_dev, HIPR_F64, (int64_t)H * W, (const uint64_t *)key, w.post))) return e;
+            if ((e = hipr_denoise_nl_means_2d(sum_dev, H, W, HIPR_F64, 7, 11, denoise_h, den, w.post))) return e;
+            if ((e = hipr_lne2d(den, H, W, W, 0, HIPR_F64, patch_size, n_dirs, table_host, flavour, nullptr, score64, w.post)))
+                return e;
+            if ((e = hipr_normalize_cast(score64, (int64_t)H * W, nullptr, score_dev, w.post))) return e;
+        } else {
+            const bool tile_local = (flavour == HIPR_FLAVOUR_F1 || flavour == HIPR_FLAVOUR_F2);
+            e = hipr_lne2d_q(sum_dev, H, W, W, 0, HIPR_F64, patch_size, n_dirs, table_host, flavour,
+                             tile_local ? nullptr : (const uint64_t *)key, score_dev, w.post);
+            if (e == HIPR_E_TABLE && !(patch_size == 11 && n_dirs == 9)) {
+                if ((e = hipr_lne2d(sum_dev, H, W, W, 0, HIPR_F64, patch_size, n_dirs, table_host, flavour,
+                                    (const uint64_t *)key, score64, w.post)))
+                    return e;
+                e = hipr_normalize_cast(score64, (int64_t)H * W, nullptr, score_dev, w.post);
+            }
+            if (e) return e;
+        }
+        HIPR_CUDA(cudaMemcpyAsync(scores_host[i], score_dev, img_bytes, cudaMemcpyDeviceToHost, w.post));
+        HIPR_CUDA(cudaEventRecord(w.post_done[k], w.post));
+    }
+    HIPR_CUDA(cudaEventRecord(w.t1, w.post));
+    HIPR_CUDA(cudaStreamSynchronize(w.post));
+    HIPR_CUDA(cudaStreamSynchronize(w.comp));
+    HIPR_CUDA(cudaStreamSynchronize(w.copy));
+    HIPR_CUDA(cudaEventElapsedTime(&w.last_ms, w.t0, w.t1));
+    t_last_ms = w.last_ms;
+    guard.dismiss();
+    return HIPR_OK;
 }
 
 extern "C" int hipr_neighbor2d_host_raw(const void *cube_host, int sample_bytes, double scale, int H, int W, int C,

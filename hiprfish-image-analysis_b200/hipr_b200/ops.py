@@ -823,6 +823,30 @@ def neighbor2d_score_host(cube, flavour="F1", patch_size=11, phi_range=9, return
     return (score, s) if return_sum else score
 
 
+def neighbor2d_score_host_batch(cubes, flavour="F1", patch_size=11, phi_range=9, denoise_h=None, out=None):
+    """A list of numpy (H, W, C) float32 cubes -> list of numpy (H, W) float32 score maps through
+    hipr_neighbor2d_host_batch: FOV i + 1 crosses PCIe while FOV i is denoised (denoise_h), scored and read back."""
+    cubes = [np.ascontiguousarray(c) for c in cubes]
+    if not cubes:
+        raise ValueError("empty batch")
+    H, W, Cn = cubes[0].shape
+    for c in cubes:
+        if c.dtype != np.float32:
+            raise TypeError("cube must be float32, got %s" % c.dtype)
+        if c.shape != (H, W, Cn):
+            raise ValueError("every cube of a batch must have the same (H, W, C)")
+    n = len(cubes)
+    tab = tables.line_table_2d(patch_size, phi_range)
+    scores = out if out is not None else [np.empty((H, W), dtype=np.float32) for _ in range(n)]
+    if len(scores) != n:
+        raise ValueError("one output array per cube")
+    cp = (C.c_void_p * n)(*[c.ctypes.data for c in cubes])
+    sp = (C.c_void_p * n)(*[s.ctypes.data for s in scores])
+    check(lib().hipr_neighbor2d_host_batch(cp, n, H, W, Cn, tab.shape[1], tab.shape[0], _tab_ptr(tab), _flavour(flavour),
+                                           float(denoise_h) if denoise_h else 0.0, sp), "neighbor2d_host_batch")
+    return scores
+
+
 def neighbor3d_score_host(cube, flavour="ME2", patch_size=11, theta_range=9, phi_range=9, out=None):
     """numpy (X, Y, Z, C) float32 -> numpy (X, Y, Z) float32 score volume, through hipr_neighbor3d_host
     (bio/...analysis.py:807-817 for 'ME2')."""

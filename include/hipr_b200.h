@@ -409,6 +409,14 @@ int hipr_neighbor3d_host(const float *cube_host, int X, int Y, int Z, int C, int
 int hipr_neighbor2d_host_denoise(const float *cube_host, int H, int W, int C, int patch_size, int n_dirs,
                                  const int32_t *table_host, int flavour, double denoise_h, float *score_host,
                                  float *sum_host);
+/* hipr_neighbor2d_host_batch: n_fov cubes (H, W, C) float32 -> n_fov score maps (H, W) float32, one FOV after
+ * another as the scripts process a sample's fields of view (syn/..._measurement.py:161-173 under the Snakefile's
+ * loop), pipelined across FOVs: FOV i + 1 is uploaded and summed while FOV i's normalisation, NL-means denoise
+ * (denoise_h > 0: syn/..._measurement.py:106-124 in full; 0: without it, as hipr_neighbor2d_host), stencil and score
+ * read-back run on a third stream.  Results are bit-identical to the single-FOV entry points. */
+int hipr_neighbor2d_host_batch(const float *const *cubes_host, int n_fov, int H, int W, int C, int patch_size,
+                               int n_dirs, const int32_t *table_host, int flavour, double denoise_h,
+                               float *const *scores_host);
 /* hipr_neighbor2d_host on raw uint16 / uint8 counts (see hipr_chansum_raw): half / a quarter of the PCIe
  * traffic of the float32 cube, same score. */
 int hipr_neighbor2d_host_raw(const void *cube_host, int sample_bytes, double scale, int H, int W, int C,

@@ -132,3 +132,25 @@ def test_chain3d_sum_denoise_score(torch_cuda, oracle):
     want = oracle.lne3d(den, "ME2")
     got = hipr_b200.neighbor3d_score(cube.cuda(), "ME2", denoise_h=0.03, denoise_distance=3)
     np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-6, atol=1e-9)
+
+
+@pytest.mark.parametrize("denoise_h", [None, 0.02])
+def test_host_batch_is_bit_identical_to_single_calls(torch_cuda, denoise_h):
+    """hipr_neighbor2d_host_batch (FOV i + 1 uploaded while FOV i is denoised / scored on a third stream, two buffer
+    sets): every score map bit-identical to the single-FOV entry point, pinned and pageable inputs, five FOVs so that
+    both buffer sets are reused."""
+    import hipr_b200
+    from hipr_b200 import synth
+    cubes = [synth.make_fov(72, 96, 95, fov_index=10 + i)[0].numpy() for i in range(5)]
+    want = [hipr_b200.neighbor2d_score_host(c, "F1", denoise_h=denoise_h) for c in cubes]
+    got = hipr_b200.neighbor2d_score_host_batch(cubes, "F1", denoise_h=denoise_h)
+    for g, w in zip(got, want):
+        assert np.array_equal(g, w)
+    pinned = []
+    for c in cubes:
+        p = hipr_b200.pinned_empty(c.shape, np.float32)
+        p[...] = c
+        pinned.append(p)
+    got2 = hipr_b200.neighbor2d_score_host_batch(pinned, "F1", denoise_h=denoise_h)
+    for g, w in zip(got2, want):
+        assert np.array_equal(g, w)
