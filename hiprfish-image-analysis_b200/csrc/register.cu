@@ -449,30 +449,41 @@ extern "C" int hipr_register_stacks(const float *const *stacks_dev, const int32_
     const int64_t ntiles = (int64_t)H * ((W + RG_PX - 1) / RG_PX);
     // (register_kernel<true> and <false> have the same function type: one flag per kernel, not per generic lambda)
     static std::atomic<uint64_t> attr_gen[2];
-    // the reference's channel layout: the pipelined straight-line kernel (clipped tiles take the general route inside it)
-    bool ref_layout = n_stacks == RefLayout::E && getenv("HIPR_REGISTER_GENERIC") == nullptr;
-    for (int e = 0; ref_layout && e < n_stacks; ++e) ref_layout = chans[e] == RefLayout::ce(e);
-    if (ref_layout) {
-        static std::atomic<uint64_t> attr_fix[2];
-        const size_t smem2 = calib_dev ? (size_t)3 * RG_PX * RefLayout::C * 4 + 16 : smem;   // flat field: two divisor tiles in rotation + 2 mbarriers
+    // the reference's channel layouts -- 95 = 32 + 23 + 20 + 14 + 6 (five lasers) and 63 = 23 + 20 + 14 + 6 (without the
+    // 405 nm excitation, syn/..._classify_spectra.py:30-33): the pipelined straight-line kernel (clipped tiles stay on
+    // its fast path, a ragged last tile takes the general route inside it)
+    auto try_layout = [&](auto layout_tag, int *handled) -> int {
+        using L = decltype(layout_tag);
+        *handled = 0;
+        if (n_stacks != L::E || getenv("HIPR_REGISTER_GENERIC") != nullptr) return HIPR_OK;
+        for (int e = 0; e < n_stacks; ++e)
+            if (chans[e] != L::ce(e)) return HIPR_OK;
+        *handled = 1;
+        static std::atomic<uint64_t> attr_fix[2];          // (per layout: the lambda is instantiated once per tag type)
+        const size_t smem2 = calib_dev ? (size_t)3 * RG_PX * L::C * 4 + 16 : smem;   // flat field: two divisor tiles in rotation + 2 mbarriers
         auto launch_fixed = [&](auto kern) -> int {
             if (first_use_on_device(attr_fix[calib_dev ? 1 : 0]))
-                HIPR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * RG_PX * RefLayout::C * 4)));
+                HIPR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * RG_PX * L::C * 4)));
             int per_sm = 1;
             HIPR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, RG_THREADS, smem2));
             if (per_sm < 1) per_sm = 1;
             int64_t grid = (int64_t)sm_count() * per_sm;
             if (grid > ntiles) grid = ntiles;
-            // a stride coprime to the tiles per row spreads the clipped edge-column tiles (general route, ~4x the
-            // cost) over all CTAs instead of the few whose stride class hits columns 0 and W - 64
+            // a stride coprime to the tiles per row spreads the edge-column tiles (predicated loads) over all CTAs
+            // instead of the few whose stride class hits columns 0 and W - 64
             auto gcd = [](int64_t a, int64_t b) { while (b) { const int64_t t = a % b; a = b; b = t; } return a; };
             while (grid > 1 && gcd(grid, (W + RG_PX - 1) / RG_PX) != 1) --grid;
             kern<<<(unsigned)grid, RG_THREADS, smem2, st>>>(g, calib_dev, cube_dev, sum_dev,
                                                            reinterpret_cast<unsigned long long *>(maxkey_dev));
             return after_launch();
         };
-        return calib_dev ? launch_fixed(register_fixed_kernel<true, RefLayout>) : launch_fixed(register_fixed_kernel<false, RefLayout>);
-    }
+        return calib_dev ? launch_fixed(register_fixed_kernel<true, L>) : launch_fixed(register_fixed_kernel<false, L>);
+    };
+    int handled = 0;
+    int rc = try_layout(RefLayout{}, &handled);
+    if (handled) return rc;
+    rc = try_layout(ChanLayout<23, 20, 14, 6>{}, &handled);
+    if (handled) return rc;
     auto launch = [&](auto kern) -> int {
         if (first_use_on_device(attr_gen[calib_dev ? 1 : 0]))
             HIPR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * RG_PX * RG_MAX_C * 4));

@@ -115,3 +115,28 @@ def test_register_interior_and_border_tiles(torch_cuda, oracle, with_cal):
             np.testing.assert_allclose(s.cpu().numpy(), want_sum, rtol=1e-14, atol=0)
         vmax, vmin = mk.values()
         assert float(vmax) == s.max().item() and float(vmin) == s.min().item()
+
+
+@pytest.mark.parametrize("chans", [CHANS, (23, 20, 14, 6)])
+@pytest.mark.parametrize("with_cal", [False, True])
+def test_register_compiled_layouts_ragged_width(torch_cuda, oracle, chans, with_cal):
+    """Both channel layouts the straight-line kernel is compiled for (95 = 32+23+20+14+6, 63 = 23+20+14+6), on a frame
+    whose width is not a multiple of the 64-pixel tile (the last tile of a row takes the general route inside the same
+    launch), with row and column shifts, with and without a flat field; and HIPR_REGISTER_GENERIC-independent parity:
+    the same inputs through a layout the kernel is not compiled for (one channel moved) agree with the oracle too."""
+    import hipr_b200
+    rng = np.random.default_rng(31 + len(chans))
+    H, W = 29, 200
+    Cn = sum(chans)
+    stacks = _stacks(rng, H, W, chans)
+    shifts = [(0, 0), (3, -2), (-4, 5), (1, 1), (-1, -7)][:len(chans)]
+    cal = (0.5 + rng.random((H, W, Cn), dtype=np.float32)).astype(np.float32) if with_cal else None
+    want_cube, want_sum = oracle.register_stacks(stacks, shifts, cal)
+    cube, s, mk = hipr_b200.register_stacks([torch_cuda.from_numpy(a).cuda() for a in stacks], shifts,
+                                            calibration=None if cal is None else torch_cuda.from_numpy(cal).cuda())
+    if with_cal:
+        assert np.array_equal(cube.cpu().numpy(), (want_cube.astype(np.float32)))   # correctly rounded float32 quotient
+        np.testing.assert_allclose(s.cpu().numpy(), want_sum, rtol=1e-13, atol=0)
+    else:
+        assert np.array_equal(cube.cpu().numpy(), want_cube.astype(np.float32))
+        np.testing.assert_allclose(s.cpu().numpy(), want_sum, rtol=1e-14, atol=0)
