@@ -20,7 +20,8 @@
 //   phase 2  warp = (plane x, half of the rows), lane k: eleven Sx[x][.][k], six sliding 6-sums along y in registers,
 //            then the 6-sum along z across lanes (shuffles), exp, accumulate weight and weighted value for six voxels
 //            per thread (first version: 8 warps, two rows / eleven voxels per thread, 154 registers: 102 ms per
-//            128 x 132 x 54 volume, latency-bound at two warps per scheduler).
+//            128 x 132 x 54 volume; 16 warps: 86 ms; 32 warps with the planes of phase 1 split in halves: 100 ms -- the
+//            redundant differences cost more than the extra warps hide).
 // Sx is double-buffered (phase 1 of shift i + 1 precedes phase 2 of shift i): one __syncthreads per shift.
 // Everything is float64, for the reason given in nlm2d.cu (the hard cutoff).
 #include "hipr_common.cuh"
@@ -126,9 +127,10 @@ nlm3d_kernel(const double *__restrict__ vp, int Yp, int Zp, int pad, int X, int 
         for (int q = 0; q < N3_NQ; ++q) {
             if (q > 0) sy += hs[q + N3_N - 1] - hs[q - 1];     // sliding window along y
             // 6-sum along z: lanes l .. l + 5 (lanes >= 27 produce unused values)
-            double box = sy;
-#pragma unroll
-            for (int w = 1; w < N3_N; ++w) box += __shfl_down_sync(0xffffffffu, sy, w);
+            // 6 = 4 + 2: pairs, quads, then quad(l) + pair(l + 4) -- three shuffles instead of five
+            const double s2 = sy + __shfl_down_sync(0xffffffffu, sy, 1);
+            const double s4 = s2 + __shfl_down_sync(0xffffffffu, s2, 2);
+            const double box = s4 + __shfl_down_sync(0xffffffffu, s2, 4);
             const double dist = fabs(box) * inv_h2s3;
             const int hi = __double2hiint(dist);
             const bool inside = (hi < 0x40140000) || (hi == 0x40140000 && __double2loint(dist) == 0);   // dist <= 5.0
