@@ -504,8 +504,9 @@ extern "C" int hipr_lne3d_dirs_host(const double *volume_padded_host, int Xp, in
 // 3-D: cube_host (X, Y, Z, C) float32 -> score_host (X, Y, Z) float32: channel sum -> /max -> edge pad -> 72 x 11 line
 // profiles -> epilogue, bio/..._analysis.py:807-817 (ME2), :900-917 (F2), :1102-1125 (F3), the cube streamed in bands
 // of whole x-planes under the channel sum.
-extern "C" int hipr_neighbor3d_host(const float *cube_host, int X, int Y, int Z, int C, int patch_size, int n_dirs,
-                                    const int32_t *table_host, int flavour, float *score_host) {
+static int neighbor3d_host_impl(const float *cube_host, int X, int Y, int Z, int C, int patch_size, int n_dirs,
+                                const int32_t *table_host, int flavour, float *score_host, double denoise_h,
+                                int denoise_distance) {
     if (!cube_host || !score_host || !table_host || X < 1 || Y < 1 || Z < 1 || C < 1) return HIPR_E_ARG;
     Workspace *wp = ws_current();
     if (!wp) return HIPR_E_NODEVICE;
@@ -549,6 +550,28 @@ extern "C" int hipr_neighbor3d_host(const float *cube_host, int X, int Y, int Z,
             return e;
         HIPR_CUDA(cudaEventRecord(w.freed[slot], w.comp));
     }
+    if (denoise_h > 0.0) {
+        // bio/..._analysis.py:452-462 in full: /max -> 3-D NL-means -> float64 stencil (the denoised volume is too smooth
+        // for the fixed-point grid, as in 2-D) -> float32 score.  aux[3]: denoised volume, then the float64 score;
+        // aux[4]: the reflect-padded copy the denoise works on
+        const int64_t wbytes = hipr_denoise_nl_means_3d_workspace(X, Y, Z, denoise_distance);
+        if (wbytes < 0) return HIPR_E_UNSUPPORTED;
+        if ((e = ws_aux(w, 3, (size_t)nvox * 8))) return e;
+        if ((e = ws_aux(w, 4, (size_t)wbytes))) return e;
+        double *den = (double *)w.aux[3];
+        if ((e = hipr_normalize(sum_dev, HIPR_F64, nvox, (const uint64_t *)key, w.comp))) return e;
+        if ((e = hipr_denoise_nl_means_3d(sum_dev, X, Y, Z, HIPR_F64, 7, denoise_distance, denoise_h, den, w.aux[4], wbytes, w.comp)))
+            return e;
+        if ((e = hipr_lne3d(den, X, Y, Z, 0, HIPR_F64, patch_size, n_dirs, table_host, flavour, nullptr, sum_dev, w.comp))) return e;
+        if ((e = hipr_normalize_cast(sum_dev, nvox, nullptr, score_dev, w.comp))) return e;
+        HIPR_CUDA(cudaMemcpyAsync(score_host, score_dev, (size_t)nvox * 4, cudaMemcpyDeviceToHost, w.comp));
+        HIPR_CUDA(cudaEventRecord(w.t1, w.comp));
+        HIPR_CUDA(cudaStreamSynchronize(w.comp));
+        HIPR_CUDA(cudaEventElapsedTime(&w.last_ms, w.t0, w.t1));
+        t_last_ms = w.last_ms;
+        guard.dismiss();
+        return HIPR_OK;
+    }
     // fixed-point stencil for the reference's (11, 9, 9) table; the float64 stencil for any other table
     e = hipr_lne3d_q(sum_dev, X, Y, Z, 0, HIPR_F64, patch_size, n_dirs, table_host, flavour, 0, (const uint64_t *)key,
                      score_dev, w.comp);
@@ -568,6 +591,19 @@ extern "C" int hipr_neighbor3d_host(const float *cube_host, int X, int Y, int Z,
     t_last_ms = w.last_ms;
     guard.dismiss();
     return HIPR_OK;
+}
+
+extern "C" int hipr_neighbor3d_host(const float *cube_host, int X, int Y, int Z, int C, int patch_size, int n_dirs,
+                                    const int32_t *table_host, int flavour, float *score_host) {
+    return neighbor3d_host_impl(cube_host, X, Y, Z, C, patch_size, n_dirs, table_host, flavour, score_host, 0.0, 11);
+}
+
+extern "C" int hipr_neighbor3d_host_denoise(const float *cube_host, int X, int Y, int Z, int C, int patch_size, int n_dirs,
+                                            const int32_t *table_host, int flavour, double denoise_h, int denoise_distance,
+                                            float *score_host) {
+    if (!(denoise_h > 0.0)) return HIPR_E_ARG;
+    return neighbor3d_host_impl(cube_host, X, Y, Z, C, patch_size, n_dirs, table_host, flavour, score_host, denoise_h,
+                                denoise_distance);
 }
 
 extern "C" int hipr_neighbor2d_host_denoise(const float *cube_host, int H, int W, int C, int patch_size, int n_dirs,

@@ -847,9 +847,11 @@ def neighbor2d_score_host_batch(cubes, flavour="F1", patch_size=11, phi_range=9,
     return scores
 
 
-def neighbor3d_score_host(cube, flavour="ME2", patch_size=11, theta_range=9, phi_range=9, out=None):
+def neighbor3d_score_host(cube, flavour="ME2", patch_size=11, theta_range=9, phi_range=9, out=None, denoise_h=None,
+                          denoise_distance=11):
     """numpy (X, Y, Z, C) float32 -> numpy (X, Y, Z) float32 score volume, through hipr_neighbor3d_host
-    (bio/...analysis.py:807-817 for 'ME2')."""
+    (bio/...analysis.py:807-817 for 'ME2'); denoise_h: with the 3-D NL-means of bio/...analysis.py:454 in the chain
+    (hipr_neighbor3d_host_denoise)."""
     cube = np.ascontiguousarray(cube)
     if cube.dtype != np.float32:
         raise TypeError("cube must be float32, got %s" % cube.dtype)
@@ -858,6 +860,11 @@ def neighbor3d_score_host(cube, flavour="ME2", patch_size=11, theta_range=9, phi
     X, Y, Z, Cn = cube.shape
     tab = tables.line_table_3d(patch_size, theta_range, phi_range)
     score = out if out is not None else np.empty((X, Y, Z), dtype=np.float32)
+    if denoise_h is not None:
+        check(lib().hipr_neighbor3d_host_denoise(cube.ctypes.data_as(C.c_void_p), X, Y, Z, Cn, tab.shape[1], tab.shape[0],
+                                                 _tab_ptr(tab), _flavour(flavour), float(denoise_h), int(denoise_distance),
+                                                 score.ctypes.data_as(C.c_void_p)), "neighbor3d_host_denoise")
+        return score
     check(lib().hipr_neighbor3d_host(cube.ctypes.data_as(C.c_void_p), X, Y, Z, Cn, tab.shape[1], tab.shape[0],
                                      _tab_ptr(tab), _flavour(flavour), score.ctypes.data_as(C.c_void_p)),
           "neighbor3d_host")

@@ -403,6 +403,12 @@ int hipr_neighbor2d_host(const float *cube_host, int H, int W, int C, int patch_
  * the cube streamed to the device in bands of x-planes under the channel sum. */
 int hipr_neighbor3d_host(const float *cube_host, int X, int Y, int Z, int C, int patch_size, int n_dirs,
                          const int32_t *table_host, int flavour, float *score_host);
+/* hipr_neighbor3d_host with the denoise of bio/..._analysis.py:454 between the normalisation and the stencil
+ * (hipr_denoise_nl_means_3d, patch 7, distance denoise_distance (11 in the reference), h = denoise_h; the float64
+ * stencil follows): lines 452-462 in full from a host cube. */
+int hipr_neighbor3d_host_denoise(const float *cube_host, int X, int Y, int Z, int C, int patch_size, int n_dirs,
+                                 const int32_t *table_host, int flavour, double denoise_h, int denoise_distance,
+                                 float *score_host);
 /* hipr_neighbor2d_host with the denoise of syn/..._measurement.py:108 between the normalisation and the stencil
  * (hipr_denoise_nl_means_2d, patch 7, distance 11, h = denoise_h; the float64 stencil follows): lines 105-124 in
  * full.  sum_host (may be NULL) receives the DENOISED normalised sum image (the scripts' image_registered_sum_nl). */

@@ -154,3 +154,16 @@ def test_host_batch_is_bit_identical_to_single_calls(torch_cuda, denoise_h):
     got2 = hipr_b200.neighbor2d_score_host_batch(pinned, "F1", denoise_h=denoise_h)
     for g, w in zip(got2, want):
         assert np.array_equal(g, w)
+
+
+def test_host_chain3d_with_denoise(torch_cuda):
+    """hipr_neighbor3d_host_denoise: host z-stack cube -> score volume with the 3-D NL-means in the chain
+    (bio/..._analysis.py:452-462), equal to the device-resident chain (which test_chain3d_sum_denoise_score holds
+    against the oracle) up to the float32 cast of the score."""
+    import hipr_b200
+    from hipr_b200 import synth
+    cube = synth.make_volume_cube(10, 12, 30, 95, seed=8)
+    want = hipr_b200.neighbor3d_score(cube.cuda(), "ME2", denoise_h=0.03, denoise_distance=3).cpu().numpy()
+    got = hipr_b200.neighbor3d_score_host(cube.numpy(), "ME2", denoise_h=0.03, denoise_distance=3)
+    assert got.dtype == np.float32
+    np.testing.assert_array_equal(got, want.astype(np.float32))
