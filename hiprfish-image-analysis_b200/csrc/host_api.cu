@@ -470,6 +470,36 @@ extern "C" int hipr_line_profile_2d_host(const double *image_padded_host, int Hp
     return HIPR_OK;
 }
 
+// line_profile_v2 (bio/neighbor.pyx:115-181) from and to host arrays: (X, Y, Z, n_dirs, P) float64, 6,336 B per voxel at
+// (11, 9, 9) -- the reference's callers chunk the volume to 100^2 / 200^2 columns for that reason
+// (bio/..._analysis.py:900-904, 1105-1112); a 100 x 100 x 64 chunk is a 4 GB result.  Bands of whole x-planes.
+extern "C" int hipr_line_profile_3d_host(const double *volume_padded_host, int Xp, int Yp, int Zp, int patch_size, int n_dirs,
+                                         const int32_t *table_host, double *out_host) {
+    if (!volume_padded_host || !out_host || patch_size < 1) return HIPR_E_ARG;
+    const int P = patch_size, X = Xp - (P - 1), Y = Yp - (P - 1), Z = Zp - (P - 1);
+    if (X < 1 || Y < 1 || Z < 1) return HIPR_E_PATCH;
+    Workspace *wp = ws_current();
+    if (!wp) return HIPR_E_NODEVICE;
+    Workspace &w = *wp;
+    std::lock_guard<std::mutex> lock(w.mu);
+    int e = ws_init(w);
+    if (e) return e;
+    DrainOnError guard(w);
+    const size_t vol_bytes = (size_t)Xp * Yp * Zp * sizeof(double);
+    if ((e = ws_aux(w, 0, vol_bytes))) return e;
+    double *vol_dev = (double *)w.aux[0];
+    HIPR_CUDA(cudaEventRecord(w.t0, w.comp));
+    HIPR_CUDA(cudaMemcpyAsync(vol_dev, volume_padded_host, vol_bytes, cudaMemcpyHostToDevice, w.comp));
+    e = banded_to_host(w, X, (int64_t)Y * Z * n_dirs * P * sizeof(double), out_host,
+                       [&](int64_t x0, int nx, void *band, cudaStream_t st) {
+                           return hipr_line_profile_3d(vol_dev + x0 * (int64_t)Yp * Zp, nx + P - 1, Yp, Zp, HIPR_F64, P, n_dirs,
+                                                       table_host, band, st);
+                       });
+    if (e) return e;
+    guard.dismiss();
+    return HIPR_OK;
+}
+
 // The same for line_profile_memory_efficient_v2 (bio/neighbor.pyx:186-263), the 3-D stencil the z-stack pipelines
 // call (bio/..._analysis.py:456, :812): padded float64 volume (Xp, Yp, Zp) in, the (X, Y, Z, n_dirs) float64
 // per-direction values out (576 B per voxel at 72 directions), in bands of whole x-planes.

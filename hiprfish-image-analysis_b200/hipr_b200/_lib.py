@@ -60,6 +60,7 @@ _SIGNATURES = {
     "hipr_neighbor2d_host": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp]),
     "hipr_line_profile_2d_host": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "hipr_lne3d_dirs_host": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "hipr_line_profile_3d_host": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "hipr_neighbor3d_host": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "hipr_neighbor3d_host_denoise": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _i, C.c_double, _i, _vp]),
     "hipr_neighbor2d_host_denoise": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, C.c_double, _vp, _vp]),

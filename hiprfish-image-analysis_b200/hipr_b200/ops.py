@@ -490,6 +490,29 @@ def lne3d_dirs_host(volume_padded, patch_size=11, theta_range=9, phi_range=9, ou
     return out
 
 
+def line_profile_3d_host(volume_padded, patch_size=11, theta_range=9, phi_range=9, out=None, pinned=False):
+    """numpy float64 (Xp, Yp, Zp) -> numpy float64 (X, Y, Z, T, P) through hipr_line_profile_3d_host
+    (line_profile_v2 for host arrays: bands of x-planes under the device -> host copy)."""
+    a = np.ascontiguousarray(volume_padded)
+    if a.dtype != np.float64:
+        raise TypeError("image_padded must be float64, got %s" % a.dtype)
+    if a.ndim != 3:
+        raise ValueError("Buffer has wrong number of dimensions (expected 3, got %d)" % a.ndim)
+    tab = tables.line_table_3d(patch_size, theta_range, phi_range)
+    T, P = tab.shape[0], tab.shape[1]
+    Xp, Yp, Zp = a.shape
+    if min(a.shape) < P:
+        raise ValueError("volume smaller than the patch")
+    shape = (Xp - P + 1, Yp - P + 1, Zp - P + 1, T, P)
+    if out is None:
+        out = torch.empty(shape, dtype=torch.float64, pin_memory=True).numpy() if pinned else np.empty(shape, dtype=np.float64)
+    elif out.shape != shape or out.dtype != np.float64 or not out.flags.c_contiguous:
+        raise ValueError("out must be a C-contiguous float64 array of shape %s" % (shape,))
+    check(lib().hipr_line_profile_3d_host(a.ctypes.data_as(C.c_void_p), Xp, Yp, Zp, P, T, _tab_ptr(tab),
+                                     out.ctypes.data_as(C.c_void_p)), "line_profile_3d_host")
+    return out
+
+
 def lne3d(volume, flavour="F2", patch_size=11, theta_range=9, phi_range=9, padded=False, maxkey=None):
     """3-D score map (X, Y, Z).  flavour 'F2' / 'F3' / 'ME2', or 'V3' (needs padded=True)."""
     v = _vol(volume, "volume")

@@ -29,8 +29,12 @@ def _run(fn, image_padded, *params):
 
 def line_profile_v2(image_padded, patch_size, theta_range, phi_range):
     """(Xp,Yp,Zp) -> (X,Y,Z,(theta_range-1)*phi_range,P) literal gather, bio/neighbor.pyx:115-181."""
+    import torch
     from hipr_b200 import ops
-    return _run(ops.line_profile_3d, image_padded, patch_size, theta_range, phi_range)
+    if isinstance(image_padded, torch.Tensor):
+        return _run(ops.line_profile_3d, image_padded, patch_size, theta_range, phi_range)
+    params = [_tables._int_arg(p, "parameter") for p in (patch_size, theta_range, phi_range)]
+    return ops.line_profile_3d_host(_as_double_2d(image_padded, 3), *params)
 
 
 def line_profile_memory_efficient_v2(image_padded, patch_size, theta_range, phi_range):

@@ -239,6 +239,10 @@ int hipr_lne3d_dirs(const void *volume_dev, int Xs, int Ys, int Zs, int padded, 
  * (page-locked out_host directly, pageable through the staging ring).  Blocking. */
 int hipr_lne3d_dirs_host(const double *volume_padded_host, int Xp, int Yp, int Zp, int patch_size,
                          int n_dirs, const int32_t *table_host, double *out_host);
+/* line_profile_v2 (bio/neighbor.pyx:115-181) from and to host arrays, same banding:
+ * out_host (X, Y, Z, n_dirs, P) float64, 6,336 B per voxel at (11, 9, 9). */
+int hipr_line_profile_3d_host(const double *volume_padded_host, int Xp, int Yp, int Zp, int patch_size,
+                              int n_dirs, const int32_t *table_host, double *out_host);
 int hipr_lne3d(const void *volume_dev, int Xs, int Ys, int Zs, int padded, int dtype,
                int patch_size, int n_dirs, const int32_t *table_host, int flavour,
                const uint64_t *maxkey_dev, void *out_dev, void *stream);

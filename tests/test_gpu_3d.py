@@ -64,6 +64,16 @@ def test_memory_efficient_v2_host_bands(torch_cuda):
         hipr_b200.lne3d_dirs_host(a.astype(np.float32), 11, 9, 9)
 
 
+def test_line_profile_v2_host_bands(torch_cuda):
+    """hipr_line_profile_3d_host: several bands of x-planes (6,336 B per voxel), bit-identical to the device operator."""
+    import hipr_b200
+    a = smooth_image((34, 40, 42), 12).astype(np.float64)          # (24, 30, 32, 72, 11) float64 = 146 MB: 5 bands
+    want = hipr_b200.line_profile_3d(_cuda(torch_cuda, a), 11, 9, 9).cpu().numpy()
+    got = hipr_b200.line_profile_3d_host(a, 11, 9, 9)
+    assert got.shape == (24, 30, 32, 72, 11) and np.array_equal(got, want)
+    assert np.array_equal(hipr_b200.line_profile_3d_host(a, 11, 9, 9, pinned=True), want)
+
+
 def test_memory_efficient_v2_flat_lines_clamped(torch_cuda, oracle):
     import neighbor
     a = np.full((15, 15, 15), 0.5)
