@@ -172,15 +172,17 @@ gather_kernel(const T *__restrict__ src, int64_t stride_a, int64_t stride_b, int
 // instruction, so a load touches one or two lines (in the kernel above the 32 lanes of a load spread over the K
 // samples of two pixels, ~11 image rows: L1-tag bound, 3.8 TB/s) and the store lands at word p * K + k (K odd: no bank
 // conflicts) -- then streams the block out, contiguous, with 16-byte stores.
-constexpr int GT_PX = 64;
 // KT > 0: K known at compile time (99 = the (11, 9) table every 2-D pipeline uses): a thread's sample offsets -- the
 // same for every block -- live in registers and its loads are issued in two batches of up to 13 before the stores
 // (the run-time-K form keeps 4 in flight and re-reads the offsets from shared memory: 0.69 ms against the 0.44 ms a
 // plain fill of the same 3.3 GB takes).
-template <typename T, int KT>
+// PX: pixels per block.  64 for the 2-D tables (K <= 128); 8 for the pinned 3-D table (KT = 792: 8 voxels x 792 samples
+// are the same 50 KB block, a warp's load covers 4 samples x 8 consecutive voxels).
+template <typename T, int KT, int PX>
 __global__ void __launch_bounds__(GA_THREADS)
-gather_tile_kernel(const T *__restrict__ src, int64_t stride_row, int64_t nrows, int rowlen, int K_rt,
-                   const __grid_constant__ Table2D offs, T *__restrict__ out) {
+gather_tile_kernel(const T *__restrict__ src, int64_t stride_a, int64_t stride_b, int inner, int64_t nrows, int rowlen,
+                   int K_rt, const __grid_constant__ Table2D offs, T *__restrict__ out) {
+    constexpr int GT_PX = PX;
     extern __shared__ __align__(16) unsigned char gt_smem[];
     const int K = KT > 0 ? KT : K_rt;
     T *tile = reinterpret_cast<T *>(gt_smem);
@@ -202,7 +204,8 @@ gather_tile_kernel(const T *__restrict__ src, int64_t stride_row, int64_t nrows,
         const int64_t row = w / chunks_per_row;
         const int c0 = (int)(w - row * chunks_per_row) * GT_PX;
         const int npx = min(GT_PX, rowlen - c0);
-        const T *sbase = src + row * stride_row + c0;
+        const int64_t ra = row / inner, rb = row - ra * inner;
+        const T *sbase = src + ra * stride_a + rb * stride_b + c0;
         if (p < npx) {
             T *tp = tile + p * K + k0;
             const T *sp = sbase + p;
@@ -295,22 +298,27 @@ int gather_launch(const T *src, int64_t stride_a, int64_t stride_b, int inner, i
     if (K < 1 || K > HIPR_MAX_TABLE) return HIPR_E_TABLE;
     Table2D offs;
     memcpy(offs.off, lin, K * sizeof(int));
-    // 2-D tables: the shared-memory block kernel, when every 64-pixel block of the output starts on 16 bytes
-    if (K <= 128 && inner == 1 && stride_b == 0 && (((uintptr_t)out) & 15u) == 0 &&
-        ((int64_t)rowlen * K * sizeof(T)) % 16 == 0 && ((int64_t)GT_PX * K * sizeof(T)) % 16 == 0) {
-        const size_t smem = (size_t)GT_PX * K * sizeof(T) + (size_t)K * sizeof(int);
+    // the shared-memory block kernel, when every block of the output starts on 16 bytes: 64-pixel blocks for the 2-D
+    // tables, 8-voxel blocks for the pinned 3-D table
+    const int px_blk = (K <= 128) ? 64 : 8;
+    // (3-D in float64 stays on the element-order kernel: measured 1.25 ms against 1.31 ms here, the 64-bit stores of 8-voxel
+    // blocks conflict four ways; float32: 0.93 -> 0.64 ms per 96 x 128 x 64 volume)
+    if ((K <= 128 || (K == 792 && sizeof(T) == 4)) && (((uintptr_t)out) & 15u) == 0 && ((int64_t)rowlen * K * sizeof(T)) % 16 == 0 &&
+        ((int64_t)px_blk * K * sizeof(T)) % 16 == 0) {
+        const size_t smem = (size_t)px_blk * K * sizeof(T) + (size_t)K * sizeof(int);
         static std::atomic<uint64_t> attr_gt{0};
         if (first_use_on_device(attr_gt)) {
-            HIPR_CUDA(cudaFuncSetAttribute(gather_tile_kernel<T, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_PX * 128 * 8 + 128 * 4));
-            HIPR_CUDA(cudaFuncSetAttribute(gather_tile_kernel<T, 99>, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_PX * 128 * 8 + 128 * 4));
+            HIPR_CUDA(cudaFuncSetAttribute(gather_tile_kernel<T, 0, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 128 * 8 + 128 * 4));
+            HIPR_CUDA(cudaFuncSetAttribute(gather_tile_kernel<T, 99, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 128 * 8 + 128 * 4));
+            HIPR_CUDA(cudaFuncSetAttribute(gather_tile_kernel<T, 792, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 792 * 8 + 792 * 4));
         }
-        auto kern = (K == 99) ? gather_tile_kernel<T, 99> : gather_tile_kernel<T, 0>;
+        auto kern = (K == 99) ? gather_tile_kernel<T, 99, 64> : (K == 792) ? gather_tile_kernel<T, 792, 8> : gather_tile_kernel<T, 0, 64>;
         int per_sm = 1;
         HIPR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, GA_THREADS, smem));
-        const int64_t work = nrows * ((rowlen + GT_PX - 1) / GT_PX);
+        const int64_t work = nrows * ((rowlen + px_blk - 1) / px_blk);
         int64_t grid = (int64_t)sm_count() * (per_sm < 1 ? 1 : per_sm);
         if (grid > work) grid = work;
-        kern<<<(unsigned)grid, GA_THREADS, smem, st>>>(src, stride_a, nrows, rowlen, K, offs, out);
+        kern<<<(unsigned)grid, GA_THREADS, smem, st>>>(src, stride_a, stride_b, inner, nrows, rowlen, K, offs, out);
         return after_launch();
     }
     int chunk = 128;
