@@ -106,16 +106,29 @@ nlm3d_kernel(const double *__restrict__ vp, int Yp, int Zp, int pad, int X, int 
     const bool lane_on = lane < N3_TZ;
     const int side = 2 * d + 1;
     const int nshift = side * side * side;
-    auto shift_off = [&](int s) -> int64_t {
-        const int tz = s % side - d, ty = (s / side) % side - d, tx = s / (side * side) - d;
-        return (int64_t)tx * plane + (int64_t)ty * Zp + tz;
+    // shifts in (tx, ty, tz) raster order, tz fastest; the linear offset of the shifted samples advances incrementally
+    // (an integer division by the run-time side length per shift cost ~80 instructions per thread and shift)
+    int64_t soff = -(int64_t)d * plane - (int64_t)d * Zp - d;
+    int cy = 0, cz = 0;                                          // ty + d, tz + d of `soff`
+    auto advance = [&](int64_t &off, int &ky, int &kz) {
+        ++off;
+        if (++kz == side) {
+            kz = 0;
+            off += Zp - side;
+            if (++ky == side) {
+                ky = 0;
+                off += plane - (int64_t)side * Zp;
+            }
+        }
     };
-    phase1(shift_off(0), 0);
+    phase1(soff, 0);
     __syncthreads();
     int buf = 0;
     for (int s = 0; s < nshift; ++s) {
-        if (s + 1 < nshift) phase1(shift_off(s + 1), buf ^ 1);
-        const int64_t soff = shift_off(s);
+        int64_t soff_next = soff;
+        int ny = cy, nz = cz;
+        advance(soff_next, ny, nz);
+        if (s + 1 < nshift) phase1(soff_next, buf ^ 1);
         const double *hcur = Sx + buf * SXN + px * N3_RY * N3_RZ + lane;
         double hs[N3_NQ + N3_N - 1];
 #pragma unroll
@@ -142,6 +155,9 @@ nlm3d_kernel(const double *__restrict__ vp, int Yp, int Zp, int pad, int X, int 
             acc_v[q] = fma(w, v, acc_v[q]);
         }
         buf ^= 1;
+        soff = soff_next;
+        cy = ny;
+        cz = nz;
         __syncthreads();
     }
     const int x = x0 + px, z = z0 + lane;
