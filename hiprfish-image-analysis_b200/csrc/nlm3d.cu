@@ -66,18 +66,18 @@ nlm3d_kernel(const double *__restrict__ vp, int Yp, int Zp, int pad, int X, int 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nzb = (Z + N3_TZ - 1) / N3_TZ, nyb = (Y + N3_TY - 1) / N3_TY;
     const int z0 = (blockIdx.x % nzb) * N3_TZ, y0 = ((blockIdx.x / nzb) % nyb) * N3_TY, x0 = (blockIdx.x / (nzb * nyb)) * N3_TX;
-    const int64_t plane = (int64_t)Yp * Zp;
+    const int plane = Yp * Zp;                 // 32-bit strides and shift offsets (the launcher checks 12 * plane < 2^31): one IMAD.WIDE per address
     // region origin in the padded volume: tile origin - offset + 1
     const double *rbase = vp + ((int64_t)(x0 + pad - N3_OFF + 1) * Yp + (y0 + pad - N3_OFF + 1)) * Zp + (z0 + pad - N3_OFF + 1);
     for (int i = tid; i < N3_RX * N3_RY * N3_RZ; i += N3_THREADS) {
         const int k = i & 31, j = (i >> 5) & 15, ii = i >> 9;
-        A[i] = rbase[ii * plane + (int64_t)j * Zp + k];
+        A[i] = rbase[(int64_t)ii * plane + (int64_t)j * Zp + k];
     }
     __syncthreads();
     // phase 1: row j = warp of the region, column k = lane
     const double *a1 = A + warp * N3_RZ + lane;
     const double *b1 = rbase + (int64_t)warp * Zp + lane;
-    auto phase1 = [&](int64_t soff, int which) {
+    auto phase1 = [&](int soff, int which) {
         double *dst = Sx + which * SXN + warp * N3_RZ + lane;
         const double *b = b1 + soff;
         double D[N3_RX];
@@ -108,16 +108,16 @@ nlm3d_kernel(const double *__restrict__ vp, int Yp, int Zp, int pad, int X, int 
     const int nshift = side * side * side;
     // shifts in (tx, ty, tz) raster order, tz fastest; the linear offset of the shifted samples advances incrementally
     // (an integer division by the run-time side length per shift cost ~80 instructions per thread and shift)
-    int64_t soff = -(int64_t)d * plane - (int64_t)d * Zp - d;
+    int soff = -d * plane - d * Zp - d;
     int cy = 0, cz = 0;                                          // ty + d, tz + d of `soff`
-    auto advance = [&](int64_t &off, int &ky, int &kz) {
+    auto advance = [&](int &off, int &ky, int &kz) {
         ++off;
         if (++kz == side) {
             kz = 0;
             off += Zp - side;
             if (++ky == side) {
                 ky = 0;
-                off += plane - (int64_t)side * Zp;
+                off += plane - side * Zp;
             }
         }
     };
@@ -125,7 +125,7 @@ nlm3d_kernel(const double *__restrict__ vp, int Yp, int Zp, int pad, int X, int 
     __syncthreads();
     int buf = 0;
     for (int s = 0; s < nshift; ++s) {
-        int64_t soff_next = soff;
+        int soff_next = soff;
         int ny = cy, nz = cz;
         advance(soff_next, ny, nz);
         if (s + 1 < nshift) phase1(soff_next, buf ^ 1);
@@ -150,7 +150,7 @@ nlm3d_kernel(const double *__restrict__ vp, int Yp, int Zp, int pad, int X, int 
             const bool on = lane_on && yb + q < N3_TY;
             double w = exp_small_neg(-dist);
             w = (inside && on) ? w : 0.0;
-            const double v = on ? __ldg(vc + soff + (int64_t)q * Zp) : 0.0;
+            const double v = on ? __ldg(vc + (soff + q * Zp)) : 0.0;
             acc_w[q] += w;
             acc_v[q] = fma(w, v, acc_v[q]);
         }
@@ -191,7 +191,7 @@ extern "C" int hipr_denoise_nl_means_3d(const void *volume_dev, int X, int Y, in
     const int64_t need = (int64_t)Xp * Yp * Zp * (int64_t)sizeof(double);
     if (!volume_dev || !out_dev || !workspace_dev) return HIPR_E_ARG;
     if (workspace_bytes < need) return HIPR_E_RANGE;
-    if ((int64_t)nxb * nyb * nzb > 0x7fffffffLL) return HIPR_E_RANGE;
+    if ((int64_t)nxb * nyb * nzb > 0x7fffffffLL || 12ll * Yp * Zp > 0x7fffffffLL) return HIPR_E_RANGE;
     cudaStream_t st = (cudaStream_t)stream;
     double *vp = (double *)workspace_dev;
     const int64_t np_ = (int64_t)Xp * Yp * Zp;
