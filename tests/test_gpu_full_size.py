@@ -100,3 +100,53 @@ def test_volume_windows_and_scale_invariance(torch_cuda, oracle):
         win = s[lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]].cpu().numpy() / gmax      # ME2's 1e-8 is relative to the global max
         want = oracle.lne3d(win, "ME2")[x - lo[0]: x - lo[0] + 12, y - lo[1]: y - lo[1] + 10, z - lo[2]: z - lo[2] + 14]
         np.testing.assert_allclose(full[x:x + 12, y:y + 10, z:z + 14], want, rtol=RTOL, atol=ATOL)
+
+
+def test_config2_registration_paste_is_exact(torch_cuda):
+    """2048 x 2048 x 95 through K0 (registration paste + channel stack + flat field + channel sum): the cube equals a
+    paste written with torch slicing bit for bit (the float32 quotient of the flat field is IEEE division), the sums
+    equal float64 sums of the float64 quotients to 1e-13 -- a whole-FOV check no CPU oracle could finish in seconds."""
+    import hipr_b200
+    torch = torch_cuda
+    H = W = 2048
+    chans = (32, 23, 20, 14, 6)
+    shifts = [(0, 0), (3, -2), (-4, 1), (2, 5), (-1, -3)]
+    g = torch.Generator(device="cuda").manual_seed(7)
+    stacks = [torch.rand((H, W, c), generator=g, device="cuda") + 0.1 for c in chans]
+    cal = torch.rand((H, W, 95), generator=g, device="cuda") + 0.5
+    want = torch.zeros((H, W, 95), device="cuda")
+    o = 0
+    for st, (dr, dc), c in zip(stacks, shifts, chans):
+        want[max(dr, 0):H + min(dr, 0), max(dc, 0):W + min(dc, 0), o:o + c] = \
+            st[max(-dr, 0):H + min(-dr, 0), max(-dc, 0):W + min(-dc, 0)]
+        o += c
+    cube, s, mk = hipr_b200.register_stacks(stacks, shifts)
+    assert torch.equal(cube, want)
+    ref = want.double().sum(2)
+    assert float(((s - ref).abs() / ref).max()) < 1e-14
+    vmax, vmin = mk.values()
+    assert float(vmax) == s.max().item() and float(vmin) == s.min().item()
+    cube_c, s_c, _ = hipr_b200.register_stacks(stacks, shifts, cal)
+    assert torch.equal(cube_c, want / cal)
+    ref_c = (want.double() / cal.double()).sum(2)
+    assert float(((s_c - ref_c).abs() / ref_c).max()) < 1e-13
+
+
+def test_config2_literal_gather_is_exact(torch_cuda):
+    """The strict drop-in output at 2048 x 2048 (3.3 GB in float64): every one of the 99 samples of every pixel equals
+    the padded image at the table's offset -- checked on the device with index arithmetic, direction by direction."""
+    import hipr_b200
+    from hipr_b200 import tables
+    torch = torch_cuda
+    H = W = 2048
+    g = torch.Generator(device="cuda").manual_seed(8)
+    pad = torch.rand((H + 10, W + 10), generator=g, device="cuda", dtype=torch.float64)
+    lp = hipr_b200.line_profile_2d(pad, 11, 9)
+    assert tuple(lp.shape) == (H, W, 9, 11)
+    tab = tables.line_table_2d(11, 9)                        # (9, 11, 2) patch coordinates
+    for t in range(9):
+        for li in range(11):
+            dy, dx = int(tab[t, li, 0]), int(tab[t, li, 1])
+            assert torch.equal(lp[:, :, t, li], pad[dy:dy + H, dx:dx + W])
+    lp32 = hipr_b200.line_profile_2d(pad.float(), 11, 9)
+    assert torch.equal(lp32[:, :, 4, 7], pad.float()[int(tab[4, 7, 0]):int(tab[4, 7, 0]) + H, int(tab[4, 7, 1]):int(tab[4, 7, 1]) + W])
