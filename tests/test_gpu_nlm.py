@@ -167,3 +167,27 @@ def test_host_chain3d_with_denoise(torch_cuda):
     got = hipr_b200.neighbor3d_score_host(cube.numpy(), "ME2", denoise_h=0.03, denoise_distance=3)
     assert got.dtype == np.float32
     np.testing.assert_array_equal(got, want.astype(np.float32))
+
+
+def test_nlm3d_large_volume_properties(torch_cuda):
+    """Sizes no numpy oracle reaches (256 x 132 x 54, 12,167 shifts): exact power-of-two scale covariance
+    (denoise(4 v, 4 h) == 4 denoise(v, h) bit for bit: every operation scales exactly), a constant volume is a fixed
+    point, the output stays inside the input's range (a convex combination), and float32 input agrees with float64."""
+    import hipr_b200
+    torch = torch_cuda
+    g = torch.Generator(device="cuda").manual_seed(21)
+    x = torch.arange(256, device="cuda", dtype=torch.float64)[:, None, None]
+    y = torch.arange(132, device="cuda", dtype=torch.float64)[None, :, None]
+    z = torch.arange(54, device="cuda", dtype=torch.float64)[None, None, :]
+    v = 0.5 + 0.2 * torch.sin(x / 9.0) * torch.cos(y / 7.0) * torch.sin(z / 5.0 + 1.0) \
+        + 0.03 * torch.rand((256, 132, 54), generator=g, device="cuda", dtype=torch.float64)
+    a = hipr_b200.denoise_nl_means(v, h=0.03)
+    b = hipr_b200.denoise_nl_means(4.0 * v, h=0.12)
+    assert torch.equal(b, 4.0 * a)
+    assert float(a.min()) >= float(v.min()) and float(a.max()) <= float(v.max())
+    assert float((a - v).abs().max()) > 1e-3                               # it does denoise
+    flat = torch.full((40, 44, 54), 0.375, device="cuda", dtype=torch.float64)
+    assert torch.equal(hipr_b200.denoise_nl_means(flat, h=0.03), flat)
+    a32 = hipr_b200.denoise_nl_means(v[:64, :66].float().contiguous(), h=0.03)
+    a64 = hipr_b200.denoise_nl_means(v[:64, :66].float().double().contiguous(), h=0.03)
+    assert float((a32.double() - a64).abs().max()) < 1e-6
