@@ -183,10 +183,14 @@ __global__ void __launch_bounds__(GA_THREADS)
 gather_tile_kernel(const T *__restrict__ src, int64_t stride_a, int64_t stride_b, int inner, int64_t nrows, int rowlen,
                    int K_rt, const __grid_constant__ Table2D offs, T *__restrict__ out) {
     constexpr int GT_PX = PX;
+    // shared-memory row stride: K, except for the 3-D table, where 796 (a multiple of 4, so rows stay 16-byte aligned)
+    // takes the 8 voxels of a store instruction off the same banks (792 = 24 * 33: 8-voxel columns collide four ways)
+    constexpr int KP_CT = (KT == 792) ? 796 : KT;
     extern __shared__ __align__(16) unsigned char gt_smem[];
     const int K = KT > 0 ? KT : K_rt;
+    const int KP = KT > 0 ? KP_CT : K_rt;
     T *tile = reinterpret_cast<T *>(gt_smem);
-    int *s_off = reinterpret_cast<int *>(gt_smem + (size_t)GT_PX * K * sizeof(T));
+    int *s_off = reinterpret_cast<int *>(gt_smem + (size_t)GT_PX * KP * sizeof(T));
     constexpr int KSTEP = GA_THREADS / GT_PX;                       // 4 samples per pass of the CTA
     constexpr int NK = KT > 0 ? (KT + KSTEP - 1) / KSTEP : 1;       // samples per thread
     const int p = threadIdx.x & (GT_PX - 1), k0 = threadIdx.x / GT_PX;
@@ -207,7 +211,7 @@ gather_tile_kernel(const T *__restrict__ src, int64_t stride_a, int64_t stride_b
         const int64_t ra = row / inner, rb = row - ra * inner;
         const T *sbase = src + ra * stride_a + rb * stride_b + c0;
         if (p < npx) {
-            T *tp = tile + p * K + k0;
+            T *tp = tile + p * KP + k0;
             const T *sp = sbase + p;
             if constexpr (KT > 0) {
                 constexpr int H1 = (NK + 1) / 2;
@@ -239,8 +243,16 @@ gather_tile_kernel(const T *__restrict__ src, int64_t stride_a, int64_t stride_b
         const int nvec = total / VEC;                      // obase is 16-byte aligned (checked by the launcher)
         const int4 *t4 = reinterpret_cast<const int4 *>(tile);
         int4 *o4 = reinterpret_cast<int4 *>(obase);
-        for (int v = threadIdx.x; v < nvec; v += GA_THREADS) __stcs(o4 + v, t4[v]);
-        for (int e = nvec * VEC + threadIdx.x; e < total; e += GA_THREADS) obase[e] = tile[e];
+        if constexpr (KT > 0 && KP_CT != KT) {
+            constexpr int VR = KT / VEC, VRP = KP_CT / VEC;          // vectors per pixel row: output, shared memory
+            for (int v = threadIdx.x; v < nvec; v += GA_THREADS) {
+                const int pr = v / VR, c = v - pr * VR;
+                __stcs(o4 + v, t4[pr * VRP + c]);
+            }
+        } else {
+            for (int v = threadIdx.x; v < nvec; v += GA_THREADS) __stcs(o4 + v, t4[v]);
+            for (int e = nvec * VEC + threadIdx.x; e < total; e += GA_THREADS) obase[e] = tile[e];
+        }
         __syncthreads();
     }
 }
@@ -303,14 +315,15 @@ int gather_launch(const T *src, int64_t stride_a, int64_t stride_b, int inner, i
     const int px_blk = (K <= 128) ? 64 : 8;
     // (3-D in float64 stays on the element-order kernel: measured 1.25 ms against 1.31 ms here, the 64-bit stores of 8-voxel
     // blocks conflict four ways; float32: 0.93 -> 0.64 ms per 96 x 128 x 64 volume)
-    if ((K <= 128 || (K == 792 && sizeof(T) == 4)) && (((uintptr_t)out) & 15u) == 0 && ((int64_t)rowlen * K * sizeof(T)) % 16 == 0 &&
+    if ((K <= 128 || K == 792) && (((uintptr_t)out) & 15u) == 0 && ((int64_t)rowlen * K * sizeof(T)) % 16 == 0 &&
         ((int64_t)px_blk * K * sizeof(T)) % 16 == 0) {
-        const size_t smem = (size_t)px_blk * K * sizeof(T) + (size_t)K * sizeof(int);
+        const int kp = (K == 792) ? 796 : K;
+        const size_t smem = (size_t)px_blk * kp * sizeof(T) + (size_t)K * sizeof(int);
         static std::atomic<uint64_t> attr_gt{0};
         if (first_use_on_device(attr_gt)) {
             HIPR_CUDA(cudaFuncSetAttribute(gather_tile_kernel<T, 0, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 128 * 8 + 128 * 4));
             HIPR_CUDA(cudaFuncSetAttribute(gather_tile_kernel<T, 99, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 128 * 8 + 128 * 4));
-            HIPR_CUDA(cudaFuncSetAttribute(gather_tile_kernel<T, 792, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 792 * 8 + 792 * 4));
+            HIPR_CUDA(cudaFuncSetAttribute(gather_tile_kernel<T, 792, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 796 * 8 + 792 * 4));
         }
         auto kern = (K == 99) ? gather_tile_kernel<T, 99, 64> : (K == 792) ? gather_tile_kernel<T, 792, 8> : gather_tile_kernel<T, 0, 64>;
         int per_sm = 1;
